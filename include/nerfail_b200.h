@@ -1,0 +1,180 @@
+/*
+ * nerfail_b200.h — C ABI of libnerfail_b200.so (sm_100a only).
+ *
+ * The reference (jiang-wenxiang/NeRFail) has no FFI layer: its hot path is eager
+ * PyTorch.  Each entry point below replaces the group of ATen ops that one
+ * reference function dispatches; the citation after "replaces:" is the
+ * reference file:line (relative to the reference root) whose arithmetic the
+ * kernel reproduces.  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to call these from the unmodified Python signatures.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all tensors are contiguous, row-major, fp32 unless stated;
+ *   - nothing is allocated behind the caller's back: outputs and workspaces are
+ *     caller-owned (the only owned state is the opaque nfb_mlp_t handle);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success or a negative NFB_E_* code; the text
+ *     of the last failure on the calling thread is nfb_last_error();
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point returns NFB_E_CUDA.
+ */
+#ifndef NERFAIL_B200_H
+#define NERFAIL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFB_OK             0
+#define NFB_E_ARG         -1   /* bad argument (null pointer, non-positive size, misalignment) */
+#define NFB_E_UNSUPPORTED -2   /* shape outside what the sm_100a kernels are built for          */
+#define NFB_E_CUDA        -3   /* CUDA runtime error (text in nfb_last_error)                    */
+
+#define NFB_ABI_VERSION    1
+
+#if defined(__GNUC__)
+#define NFB_API __attribute__((visibility("default")))
+#else
+#define NFB_API
+#endif
+
+NFB_API int         nfb_abi_version(void);
+NFB_API const char* nfb_last_error(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+NFB_API uint64_t    nfb_launch_count(void);
+/* compute capability of the current device as major*10+minor, or NFB_E_CUDA */
+NFB_API int         nfb_device_cc(void);
+
+/* ------------------------------------------------------------------------- */
+/* A. NeRF render path                                                        */
+/* ------------------------------------------------------------------------- */
+
+/* Pinhole rays for one camera.
+ * replaces: run_nerf_helpers.py:157-166 (get_rays) + run_nerf.py:102-123 (viewdirs, [N,11] ray batch)
+ * K_host: 3x3 row-major doubles on the HOST (fx, 0, cx, 0, fy, cy, ...); c2w_host: 3x4 row-major floats on the HOST.
+ * rays: [H*W, 11] = o(3) d(3) near far viewdir(3).                                                    */
+NFB_API int nfb_get_rays(int H, int W, const double* K_host, const float* c2w_host,
+                 float near_, float far_, float* rays, void* stream);
+
+/* Coarse depths. replaces: run_nerf.py:357-379 (linspace / lindisp / stratified jitter)
+ * rays [R,11]; t_rand [R,S] uniform numbers or NULL (perturb == 0); z_vals out [R,S].               */
+NFB_API int nfb_coarse_z(const float* rays, int R, int S, int lindisp, const float* t_rand,
+                 float* z_vals, void* stream);
+
+/* Opaque network handle: bf16 weight images pre-swizzled for tcgen05 + fp32 biases and heads. */
+typedef struct nfb_mlp nfb_mlp_t;
+
+/* replaces: run_nerf_helpers.py:72-98 (NeRF.__init__).  The fused kernel is built for the
+ * reference's one shipped architecture: D=8, W=256, input_ch=63, input_ch_views=27, skips=[4],
+ * use_viewdirs=True (configs/lego.txt via run_nerf.py:181-198); anything else -> NFB_E_UNSUPPORTED
+ * (the host side then uses the layer-wise nfb_linear_* path).                                       */
+NFB_API int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_views, int skip);
+/* params: flat fp32 device buffer holding the state_dict tensors in this order, each row-major
+ * [out,in] then bias: pts_linears.0..7, views_linears.0, feature_linear, alpha_linear, rgb_linear
+ * (the nn.Module registration order of run_nerf_helpers.py:82-96).  Call again after optimizer.step. */
+NFB_API int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* stream);
+NFB_API int nfb_mlp_destroy(nfb_mlp_t* h);
+NFB_API int64_t nfb_mlp_param_count(const nfb_mlp_t* h);
+
+/* Fused positional-encoding + 8x256 skip MLP, bf16 tcgen05 MMA with fp32 TMEM accumulation.
+ * replaces: run_nerf.py:37-51 (run_network) + run_nerf_helpers.py:36-50 (embed) + :100-123 (NeRF.forward)
+ *   mode 0: pts  [R*S,3] explicit points,  dirs [R,3] unit view directions
+ *   mode 1: pts  = NULL; rays [R,11], z_vals [R,S]  -> pts = o + d*z formed in-kernel (run_nerf.py:381)
+ * raw out [R*S,4] = (rgb logits, sigma), fp32.                                                        */
+NFB_API int nfb_mlp_fwd(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs,
+                const float* rays, const float* z_vals, int R, int S, float* raw, void* stream);
+
+/* 0 = healthy.  NFB_E_CUDA if a pipeline barrier inside the fused kernel timed out since the last call
+ * (the kernel bails out instead of hanging the GPU; its outputs are then invalid).  Synchronises the device. */
+NFB_API int nfb_mlp_status(nfb_mlp_t* h);
+/* Validation entry: run only the first nsteps (1..10) MMA steps of the fused kernel and dump the fp32
+ * post-activation values of the last executed step to dbg [R*S,256] (128 columns for the view layer).     */
+NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs,
+                      const float* rays, const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg,
+                      void* stream);
+
+/* Positional encoding to HBM (layer-wise fp32 path only).
+ * replaces: run_nerf_helpers.py:36-50.  x [M,3] -> out [M, 3+6*L] at column offset col0 of a row pitch ld. */
+NFB_API int nfb_embed(const float* x, int64_t M, int L, float* out, int ld, int col0, int64_t row_repeat, void* stream);
+
+/* fp32 layer primitives (exact-parity / training path; CUDA-core FFMA, fp32 accumulate).
+ * replaces: the addmm / relu / autograd pairs of run_nerf_helpers.py:100-123.
+ * Every matrix carries its row pitch (ld*) so that torch.cat along features and column slices of a
+ * weight are views: e.g. the skip layer's dX only for h uses (Wt + 63, ldw = 319, K = 256).
+ *   fwd       : Y[M,N] = act(X[M,K] * W[N,K]^T + b)
+ *   bwd_data  : dX[M,K] (+)= (dY o mask) * W         mask = (Y > 0) when relu (Y = the layer's output)
+ *   bwd_weight: dW[N,K] = (dY o mask)^T * X ; db[N] = column sums of (dY o mask)   (db may be NULL)
+ *               split over M into a caller workspace and reduced in a fixed order (deterministic).    */
+NFB_API int nfb_linear_fwd(const float* X, int ldx, const float* Wt, int ldw, const float* b, int64_t M, int N, int K,
+                   int relu, float* Y, int ldy, void* stream);
+NFB_API int nfb_linear_bwd_data(const float* dY, int lddy, const float* Y, int ldy, int relu, const float* Wt, int ldw,
+                        int64_t M, int N, int K, float* dX, int lddx, int accumulate, void* stream);
+NFB_API int nfb_linear_bwd_weight(const float* dY, int lddy, const float* Y, int ldy, int relu, const float* X, int ldx,
+                          int64_t M, int N, int K, float* dW, int lddw, float* db,
+                          float* workspace, int64_t workspace_bytes, void* stream);
+NFB_API int64_t nfb_linear_bwd_weight_workspace(int64_t M, int N, int K);
+
+/* Alpha compositing. replaces: run_nerf.py:262-305 (raw2outputs) and, when pts_max != NULL,
+ * nerf_to_coord.py:418-421 (arg-max-weight point o + d*z[argmax], first maximum wins).
+ * raw [R,S,4], z_vals [R,S], rays_d [R,3] (taken from rays+3 with pitch ray_pitch floats), noise [R,S] or NULL.
+ * Outputs (any may be NULL except weights): rgb_map [R,3], disp [R], acc [R], weights [R,S], depth [R],
+ * pts_max [R,3] (needs rays_o = rays_d - 3 floats, i.e. pass a [R,11] ray batch).                    */
+NFB_API int nfb_composite_fwd(const float* raw, const float* z_vals, const float* rays_d, int ray_pitch,
+                      const float* noise, int R, int S, int white_bkgd,
+                      float* rgb_map, float* disp, float* acc, float* weights, float* depth,
+                      float* pts_max, void* stream);
+/* Analytic backward of the above (suffix-sum form). Any g_* may be NULL (= zero). g_raw out [R,S,4]. */
+NFB_API int nfb_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, int ray_pitch,
+                      const float* noise, int R, int S, int white_bkgd,
+                      const float* g_rgb, const float* g_disp, const float* g_acc,
+                      const float* g_weights, const float* g_depth, float* g_raw, void* stream);
+
+/* Inverse-CDF sampling. replaces: run_nerf_helpers.py:200-243 (sample_pdf).
+ * bins [R,nb], weights [R,nb-1] (row pitch w_pitch floats), u [R,N] or NULL (det: linspace(0,1,N)).
+ * samples out [R,N]; inds out [R,N] int32 (the searchsorted result, for the index-parity tests) or NULL. */
+NFB_API int nfb_sample_pdf(const float* bins, const float* weights, int w_pitch, const float* u,
+                   int R, int nb, int N, float* samples, int32_t* inds, void* stream);
+
+/* Fused hierarchical step. replaces: run_nerf.py:392-396 + :412
+ * (z_mid, sample_pdf on weights[...,1:-1], sort(cat(z_vals, z_samples)), z_std).
+ * z_coarse [R,Sc], weights [R,Sc], u [R,N] or NULL -> z_fine [R,Sc+N] ascending, z_samples [R,N] (or NULL),
+ * z_std [R] (or NULL).  Requires 3 <= Sc <= 128, Sc+N <= 512.                                         */
+NFB_API int nfb_hierarchical(const float* z_coarse, const float* weights, const float* u, int R, int Sc, int N,
+                     float* z_fine, float* z_samples, float* z_std, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* B. GaussNet path                                                            */
+/* ------------------------------------------------------------------------- */
+
+/* Exact brute-force 8-NN (fp32 direct-difference distances, ascending, ties -> lowest index).
+ * replaces: create_index_and_dist.py:126-145 (cdist + sort + running top-8 merge).
+ * query [Q,3], cand [C,3] -> out_dist [Q,8] fp32, out_idx [Q,8] fp32 (the reference stores indices as
+ * float32, :148-151; C < 2^24 required) and/or out_idx_i32 [Q,8].                                      */
+NFB_API int nfb_knn8(const float* query, int64_t Q, const float* cand, int64_t C,
+             float* out_dist, float* out_idx, int32_t* out_idx_i32, void* stream);
+
+/* replaces: model/GaussNet.py:169-186 (create_gauss_w.forward).
+ * dist_idx [B,2,HW,8] -> i_w [B,2,HW,8] (ch0 = weights, ch1 = indices copied).                        */
+NFB_API int nfb_gauss_weights(const float* dist_idx, int64_t B, int64_t HW, float c, float* i_w, void* stream);
+
+/* replaces: model/GaussNet.py:53-119 (gather, weight, sum, alpha, eps-clip, composite on the original).
+ * table [T,4]; w_idx [B,2,HW,8]; ori [B,HW,4] uint8; eps < 0 means "no clip" (epsilon=None).
+ * x out [B,HW,4]; x_rgba out [B,HW,4]; minmax out [2] (running min / max of alpha*x_rgb where alpha>0,
+ * updated with atomics, replaces the host-synchronising :89-103) or NULL.                             */
+NFB_API int nfb_gauss_gather_fwd(const float* table, int64_t T, const float* w_idx, const uint8_t* ori,
+                         int64_t B, int64_t HW, float eps, float* x, float* x_rgba, float* minmax,
+                         void* stream);
+/* Backward of the above w.r.t. table: warp-aggregated red.global.add.v4.f32 scatter.
+ * g_x, g_xrgba [B,HW,4] (either may be NULL); x is the saved forward output; g_table [T,4] is
+ * ACCUMULATED into (caller zeroes it).                                                               */
+NFB_API int nfb_gauss_scatter_bwd(const float* g_x, const float* g_xrgba, const float* x, const float* w_idx,
+                          const uint8_t* ori, int64_t B, int64_t HW, float eps, int64_t T,
+                          float* g_table, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFAIL_B200_H */

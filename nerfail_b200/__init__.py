@@ -1,0 +1,18 @@
+"""nerfail_b200 — B200-native (sm_100a) kernels behind NeRFail's differentiable-rendering API.
+
+Drop-in names (same signatures as the reference):
+    render, render_rays, run_network, raw2outputs, sample_pdf, batchify, batchify_rays, create_nerf,
+    NeRF, get_embedder, get_rays, gauss_net, create_gauss_w
+Importing the package does not need a GPU; calling any op does (there is no CPU fallback).
+"""
+from .nerf import NeRF, Embedder, get_embedder, get_rays, get_rays_np, ndc_rays, sample_pdf, img2mse, mse2psnr, to8b
+from .render import (render, render_rays, run_network, raw2outputs, batchify, batchify_rays, render_path,
+                     create_nerf, NetworkQuery)
+from .gauss import gauss_net, create_gauss_w, knn_index_and_dist
+
+__all__ = [
+    "NeRF", "Embedder", "get_embedder", "get_rays", "get_rays_np", "ndc_rays", "sample_pdf", "img2mse", "mse2psnr",
+    "to8b", "render", "render_rays", "run_network", "raw2outputs", "batchify", "batchify_rays", "render_path",
+    "create_nerf", "NetworkQuery", "gauss_net", "create_gauss_w", "knn_index_and_dist",
+]
+__version__ = "0.1.0"

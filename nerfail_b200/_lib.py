@@ -1,0 +1,102 @@
+"""ctypes binding of libnerfail_b200.so (the C ABI declared in include/nerfail_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised.  Nothing here imports or executes anything under oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libnerfail_b200.so"
+_lib = None
+
+c_f32p = C.c_void_p
+c_i64 = C.c_int64
+c_int = C.c_int
+c_ptr = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol of include/nerfail_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "nfb_abi_version": (c_int, []),
+    "nfb_last_error": (C.c_char_p, []),
+    "nfb_launch_count": (C.c_uint64, []),
+    "nfb_device_cc": (c_int, []),
+    "nfb_get_rays": (c_int, [c_int, c_int, c_ptr, c_ptr, C.c_float, C.c_float, c_ptr, c_ptr]),
+    "nfb_coarse_z": (c_int, [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "nfb_mlp_create": (c_int, [C.POINTER(c_ptr), c_int, c_int, c_int, c_int, c_int]),
+    "nfb_mlp_update": (c_int, [c_ptr, c_ptr, c_i64, c_ptr]),
+    "nfb_mlp_destroy": (c_int, [c_ptr]),
+    "nfb_mlp_param_count": (c_i64, [c_ptr]),
+    "nfb_mlp_fwd": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr]),
+    "nfb_mlp_status": (c_int, [c_ptr]),
+    "nfb_mlp_fwd_debug": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr]),
+    "nfb_embed": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_int, c_i64, c_ptr]),
+    "nfb_linear_fwd": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_i64, c_int, c_int, c_int, c_ptr, c_int, c_ptr]),
+    "nfb_linear_bwd_data": (c_int, [c_ptr, c_int, c_ptr, c_int, c_int, c_ptr, c_int, c_i64, c_int, c_int, c_ptr, c_int, c_int, c_ptr]),
+    "nfb_linear_bwd_weight": (c_int, [c_ptr, c_int, c_ptr, c_int, c_int, c_ptr, c_int, c_i64, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_ptr]),
+    "nfb_linear_bwd_weight_workspace": (c_i64, [c_i64, c_int, c_int]),
+    "nfb_composite_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_composite_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_sample_pdf": (c_int, [c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "nfb_hierarchical": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_knn8": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_gauss_weights": (c_int, [c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr]),
+    "nfb_gauss_gather_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_gauss_scatter_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_i64, c_ptr, c_ptr]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once). Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -m nerfail_b200.build` "
+            "(nerfail_b200 has no CPU or PyTorch fallback)")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.nfb_abi_version() != 1:
+        raise RuntimeError("libnerfail_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load().nfb_last_error() or b"").decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        names = {-1: "NFB_E_ARG", -2: "NFB_E_UNSUPPORTED", -3: "NFB_E_CUDA"}
+        raise RuntimeError(f"{what} failed with {names.get(rc, rc)}: {last_error()}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    """Device pointer of a contiguous CUDA tensor (None passes NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("nerfail_b200 kernels need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("nerfail_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().nfb_launch_count())

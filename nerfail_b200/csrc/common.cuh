@@ -1,0 +1,65 @@
+// Shared helpers for libnerfail_b200 (sm_100a).  Host-side error plumbing + small device utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/nerfail_b200.h"
+
+namespace nfb {
+
+// ---- host: error text + launch accounting --------------------------------------------------------
+char* err_buf();                       // thread-local, 512 bytes
+int   fail(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(NFB_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return NFB_OK;
+}
+
+#define NFB_CUDA(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) return nfb::fail(NFB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define NFB_REQUIRE(cond, ...)                                  \
+  do {                                                          \
+    if (!(cond)) return nfb::fail(NFB_E_ARG, __VA_ARGS__);      \
+  } while (0)
+
+int sm_count();   // cached multiprocessor count of the current device (148 on B200)
+
+// ---- device ------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// streaming 128-bit load that does not allocate in L1 (read-once inputs)
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace nfb

@@ -1,0 +1,253 @@
+// GaussNet: Gaussian weights, 8-neighbour weighted gather (forward) and warp-aggregated scatter (backward).
+//
+// Reference arithmetic: model/GaussNet.py:169-186 (create_gauss_w.forward), :53-119 (gauss_net.forward up
+// to x_rgba).  HBM/L2-bound: 228 B/pixel each way; the 30.7 MB [P*H*W,4] table is L2
+// resident on B200, so the gathers and the red.global.add.v4.f32 scatters are L2 traffic and the
+// streaming operands (weights, indices, original image, outputs) are read/written exactly once with
+// 128-bit accesses.
+#include "common.cuh"
+
+namespace nfb {
+
+__global__ void __launch_bounds__(256)
+gauss_weights_kernel(const float* __restrict__ di, int64_t B, int64_t HW, float c, float* __restrict__ out) {
+  const int64_t n = B * HW;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, q = p % HW;
+    const float4* dsrc = reinterpret_cast<const float4*>(di + ((b * 2 + 0) * HW + q) * 8);
+    const float4* isrc = reinterpret_cast<const float4*>(di + ((b * 2 + 1) * HW + q) * 8);
+    float4* wdst = reinterpret_cast<float4*>(out + ((b * 2 + 0) * HW + q) * 8);
+    float4* idst = reinterpret_cast<float4*>(out + ((b * 2 + 1) * HW + q) * 8);
+    const float4 d0 = ld_stream4(dsrc), d1 = ld_stream4(dsrc + 1);
+    float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float t = __fdiv_rn(d[k], c);
+      d[k] = expf(-__fdiv_rn(__fmul_rn(t, t), 2.f));        // exp(-(dist/c)^2 / 2)   :174-175
+      s = __fadd_rn(s, d[k]);
+    }
+    const float dq = __fadd_rn(s, 0.001f);                   // :178
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = (s > 0.f) ? __fdiv_rn(d[k], dq) : 0.f;   // :181
+    st_stream4(wdst, make_float4(d[0], d[1], d[2], d[3]));
+    st_stream4(wdst + 1, make_float4(d[4], d[5], d[6], d[7]));
+    st_stream4(idst, ld_stream4(isrc));
+    st_stream4(idst + 1, ld_stream4(isrc + 1));
+  }
+}
+
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {   // valid for any sign mix
+  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+struct PixelIn {
+  float w[8];
+  int idx[8];
+  float ori[4];
+};
+
+__device__ __forceinline__ PixelIn load_pixel(const float* __restrict__ w_idx, const uint8_t* __restrict__ ori,
+                                              int64_t b, int64_t q, int64_t HW) {
+  PixelIn px;
+  const float4* ws = reinterpret_cast<const float4*>(w_idx + ((b * 2 + 0) * HW + q) * 8);
+  const float4* is = reinterpret_cast<const float4*>(w_idx + ((b * 2 + 1) * HW + q) * 8);
+  const float4 w0 = ld_stream4(ws), w1 = ld_stream4(ws + 1), i0 = ld_stream4(is), i1 = ld_stream4(is + 1);
+  px.w[0] = w0.x; px.w[1] = w0.y; px.w[2] = w0.z; px.w[3] = w0.w;
+  px.w[4] = w1.x; px.w[5] = w1.y; px.w[6] = w1.z; px.w[7] = w1.w;
+  px.idx[0] = (int)i0.x; px.idx[1] = (int)i0.y; px.idx[2] = (int)i0.z; px.idx[3] = (int)i0.w;   // .type(torch.long) :62
+  px.idx[4] = (int)i1.x; px.idx[5] = (int)i1.y; px.idx[6] = (int)i1.z; px.idx[7] = (int)i1.w;
+  const uchar4 o = *reinterpret_cast<const uchar4*>(ori + (b * HW + q) * 4);
+  px.ori[0] = (float)o.x; px.ori[1] = (float)o.y; px.ori[2] = (float)o.z; px.ori[3] = (float)o.w;
+  return px;
+}
+
+__global__ void __launch_bounds__(256)
+gauss_gather_fwd_kernel(const float4* __restrict__ table, int64_t T, const float* __restrict__ w_idx,
+                        const uint8_t* __restrict__ ori, int64_t B, int64_t HW, float eps,
+                        float4* __restrict__ x_out, float4* __restrict__ xrgba_out, float* __restrict__ minmax) {
+  const int64_t n = B * HW;
+  float vmin = 0.f, vmax = 0.f;
+  bool any = false;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, q = p % HW;
+    const PixelIn px = load_pixel(w_idx, ori, b, q, HW);
+    float4 rows[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {      // issue all 8 gathers before the first use
+      int id = px.idx[k];
+      id = id < 0 ? 0 : (id >= T ? (int)(T - 1) : id);
+      rows[k] = __ldg(table + id);
+    }
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {      // (x * w).sum(-2), k ascending   :81-83
+      x.x = __fadd_rn(x.x, __fmul_rn(rows[k].x, px.w[k]));
+      x.y = __fadd_rn(x.y, __fmul_rn(rows[k].y, px.w[k]));
+      x.z = __fadd_rn(x.z, __fmul_rn(rows[k].z, px.w[k]));
+      x.w = __fadd_rn(x.w, __fmul_rn(rows[k].w, px.w[k]));
+    }
+    const float alpha = __fdiv_rn(x.w, 255.f);                                   // :85
+    float pr[3] = {__fmul_rn(x.x, alpha), __fmul_rn(x.y, alpha), __fmul_rn(x.z, alpha)};
+    if (minmax) {                                                                // :89-103 without the host sync
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const float v = (alpha > 0.f) ? pr[ch] : 0.f;
+        if (!any) { vmin = v; vmax = v; any = true; }
+        vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+      }
+    }
+    float4 out;
+    float* o = &out.x;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = pr[ch];
+      if (eps >= 0.f) v = fminf(fmaxf(v, -eps), eps);                            // :109
+      v = __fadd_rn(px.ori[ch], v);                                              // :107 / :110
+      if (!(px.ori[3] > 0.f)) v = 0.f;                                           // :112-113
+      o[ch] = fminf(fmaxf(v, 0.f), 255.f);                                       // :119
+    }
+    out.w = fminf(fmaxf(px.ori[3], 0.f), 255.f);
+    st_stream4(x_out + p, x);
+    st_stream4(xrgba_out + p, out);
+  }
+  if (minmax) {
+    unsigned have = __ballot_sync(FULL, any);
+    if (have) {
+      const int src = __ffs(have) - 1;
+      const float fill_min = __shfl_sync(FULL, vmin, src), fill_max = __shfl_sync(FULL, vmax, src);
+      if (!any) { vmin = fill_min; vmax = fill_max; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(FULL, vmin, o));
+        vmax = fmaxf(vmax, __shfl_xor_sync(FULL, vmax, o));
+      }
+      if ((threadIdx.x & 31) == 0) { atomic_min_f(minmax, vmin); atomic_max_f(minmax + 1, vmax); }
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// One thread per pixel computes G = dL/dx (4 channels); the 8 contributions w_k * G go to table rows idx_k.
+// Lanes of a warp that hit the same row at the same k are merged (match.any) and only the lowest lane issues
+// the 128-bit reduction, so neighbouring pixels that share neighbours cost one L2 atomic instead of several.
+__global__ void __launch_bounds__(256)
+gauss_scatter_bwd_kernel(const float4* __restrict__ g_x, const float4* __restrict__ g_xrgba,
+                         const float4* __restrict__ x_saved, const float* __restrict__ w_idx,
+                         const uint8_t* __restrict__ ori, int64_t B, int64_t HW, float eps, int64_t T,
+                         float4* __restrict__ g_table) {
+  const int64_t n = B * HW;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_round = (n + 31) & ~(int64_t)31;     // whole warps stay convergent for the shuffles
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_round; p += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = p < n;
+    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+    PixelIn px;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { px.w[k] = 0.f; px.idx[k] = -1 - lane; }
+    if (live) {
+      const int64_t b = p / HW, q = p % HW;
+      px = load_pixel(w_idx, ori, b, q, HW);
+      if (g_x) G = ld_stream4(g_x + p);
+      if (g_xrgba) {
+        const float4 go = ld_stream4(g_xrgba + p);
+        const float4 x = ld_stream4(x_saved + p);
+        const float alpha = __fdiv_rn(x.w, 255.f);
+        const float xs[3] = {x.x, x.y, x.z};
+        const float gs[3] = {go.x, go.y, go.z};
+        float* Gp = &G.x;
+        float g_alpha = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float pr = __fmul_rn(xs[ch], alpha);
+          float v = pr;
+          bool pass = true;
+          if (eps >= 0.f) { pass = (pr >= -eps) && (pr <= eps); v = fminf(fmaxf(pr, -eps), eps); }
+          v = __fadd_rn(px.ori[ch], v);
+          pass = pass && (px.ori[3] > 0.f) && (v >= 0.f) && (v <= 255.f);   // torch.clip passes grad on the closed interval
+          if (pass) { Gp[ch] += gs[ch] * alpha; g_alpha += gs[ch] * xs[ch]; }
+        }
+        G.w += g_alpha / 255.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int id = px.idx[k];
+      if (live) id = id < 0 ? 0 : (id >= T ? (int)(T - 1) : id);
+      float4 v = make_float4(G.x * px.w[k], G.y * px.w[k], G.z * px.w[k], G.w * px.w[k]);
+      const unsigned peers = __match_any_sync(FULL, id);
+      const int leader = __ffs(peers) - 1;
+      unsigned rem = peers & ~(1u << leader);
+      while (__any_sync(FULL, rem != 0)) {
+        const int src = rem ? (__ffs(rem) - 1) : lane;
+        const float ox = __shfl_sync(FULL, v.x, src), oy = __shfl_sync(FULL, v.y, src);
+        const float oz = __shfl_sync(FULL, v.z, src), ow = __shfl_sync(FULL, v.w, src);
+        if (lane == leader && rem) { v.x += ox; v.y += oy; v.z += oz; v.w += ow; }
+        rem &= rem - 1;
+      }
+      if (live && lane == leader) red_add_v4(g_table + id, v);
+    }
+  }
+}
+
+static int stream_grid(int64_t items) {
+  int64_t blocks = (items + 255) / 256;
+  int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace nfb
+
+extern "C" {
+
+int nfb_gauss_weights(const float* dist_idx, int64_t B, int64_t HW, float c, float* i_w, void* stream) {
+  NFB_REQUIRE(dist_idx && i_w && B >= 0 && HW >= 0 && c != 0.f, "gauss_weights: bad argument");
+  NFB_REQUIRE(((reinterpret_cast<uintptr_t>(dist_idx) | reinterpret_cast<uintptr_t>(i_w)) & 15) == 0,
+              "gauss_weights: buffers must be 16-byte aligned");
+  if (B * HW == 0) return NFB_OK;
+  nfb::gauss_weights_kernel<<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(dist_idx, B, HW, c, i_w);
+  return nfb::check_launch("gauss_weights");
+}
+
+int nfb_gauss_gather_fwd(const float* table, int64_t T, const float* w_idx, const uint8_t* ori,
+                         int64_t B, int64_t HW, float eps, float* x, float* x_rgba, float* minmax, void* stream) {
+  NFB_REQUIRE(table && w_idx && ori && x && x_rgba, "gauss_gather_fwd: null pointer");
+  NFB_REQUIRE(T > 0 && T < (1 << 24) + 1 && B >= 0 && HW >= 0, "gauss_gather_fwd: T=%lld B=%lld HW=%lld", (long long)T, (long long)B, (long long)HW);
+  NFB_REQUIRE(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(w_idx) | reinterpret_cast<uintptr_t>(x) |
+                reinterpret_cast<uintptr_t>(x_rgba)) & 15) == 0 && (reinterpret_cast<uintptr_t>(ori) & 3) == 0,
+              "gauss_gather_fwd: buffers must be 16-byte aligned (ori: 4)");
+  if (B * HW == 0) return NFB_OK;
+  nfb::gauss_gather_fwd_kernel<<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(table), T, w_idx, ori, B, HW, eps,
+      reinterpret_cast<float4*>(x), reinterpret_cast<float4*>(x_rgba), minmax);
+  return nfb::check_launch("gauss_gather_fwd");
+}
+
+int nfb_gauss_scatter_bwd(const float* g_x, const float* g_xrgba, const float* x, const float* w_idx,
+                          const uint8_t* ori, int64_t B, int64_t HW, float eps, int64_t T,
+                          float* g_table, void* stream) {
+  NFB_REQUIRE(w_idx && ori && g_table && (g_x || g_xrgba), "gauss_scatter_bwd: null pointer");
+  NFB_REQUIRE(!g_xrgba || x, "gauss_scatter_bwd: x (saved forward output) is required with g_xrgba");
+  NFB_REQUIRE(T > 0 && B >= 0 && HW >= 0, "gauss_scatter_bwd: bad size");
+  NFB_REQUIRE(((reinterpret_cast<uintptr_t>(g_table) | reinterpret_cast<uintptr_t>(w_idx) | reinterpret_cast<uintptr_t>(g_x) |
+                reinterpret_cast<uintptr_t>(g_xrgba) | reinterpret_cast<uintptr_t>(x)) & 15) == 0,
+              "gauss_scatter_bwd: buffers must be 16-byte aligned");
+  if (B * HW == 0) return NFB_OK;
+  nfb::gauss_scatter_bwd_kernel<<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(g_x), reinterpret_cast<const float4*>(g_xrgba),
+      reinterpret_cast<const float4*>(x), w_idx, ori, B, HW, eps, T, reinterpret_cast<float4*>(g_table));
+  return nfb::check_launch("gauss_scatter_bwd");
+}
+
+}  // extern "C"

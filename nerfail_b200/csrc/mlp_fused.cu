@@ -1,0 +1,655 @@
+// Fused positional encoding + 8x256 skip MLP (+ alpha / feature / view / rgb heads) on tcgen05 tensor cores.
+//
+// Reference arithmetic: Create_spatial_point_set/nerf_pytorch/run_nerf.py:37-51 (run_network),
+// run_nerf_helpers.py:36-50 (Embedder), :100-123 (NeRF.forward), run_nerf.py:381 (pts = o + d*z).
+//
+// Data flow for one 128-sample tile (one CTA works on two tiles, "slots", in ping-pong):
+//   input stage : each epilogue thread owns one sample (= one TMEM lane): builds the 63 (+1 pad) positional
+//                 features in registers and writes them as bf16 into the slot's PE chunk (128x64, K-major,
+//                 128-byte swizzle) -> A operand of layer 0 and, again, of the skip layer 5.
+//   layer l     : the MMA thread issues tcgen05.mma (M=128, N=128 per weight half, K=16) with
+//                 A = the slot's activation chunks in shared memory, B = a 16 KB weight block streamed by
+//                 the bulk-copy engine (cp.async.bulk + mbarrier tx-count) from a pre-swizzled bf16 image,
+//                 D = 128x256 fp32 accumulator in TMEM (columns slot*256 ..).
+//   epilogue l  : 4 warps read the accumulator with tcgen05.ld (32x32b.x32), add the fp32 bias, relu,
+//                 round to bf16 and overwrite the slot's activation chunks in place (the MMAs that read
+//                 them have completed).  Layer 7's epilogue also forms sigma = w_alpha . h + b in fp32;
+//                 the view layer's epilogue forms the three rgb logits in fp32 and stores the float4 raw.
+//   While slot 0 is in its epilogue the tensor core runs slot 1's layer, and vice versa.
+//
+// Activations never leave the SM; HBM traffic is 16 B read + 16 B written per sample.
+#include "common.cuh"
+
+namespace nfb {
+
+// ---------------------------------------------------------------------------------------------------
+// Architecture constants (the reference's one shipped NeRF: configs/lego.txt through run_nerf.py:181-198)
+// ---------------------------------------------------------------------------------------------------
+constexpr int W_ = 256;            // netwidth
+constexpr int L_PTS = 10;          // multires      -> 63 features
+constexpr int L_DIR = 4;           // multires_views-> 27 features
+constexpr int CH_PTS = 63, CH_DIR = 27;
+constexpr int TILE_M = 128;
+constexpr int KCH = 64;            // K elements per smem chunk (= one 128-byte swizzle row of bf16)
+constexpr int CHUNK_BYTES = TILE_M * KCH * 2;     // 16 KB: activation chunk and weight block alike
+constexpr int NSTEP = 10;          // MMA steps per tile: L0..L7, feature, views
+constexpr int NSTAGE = 4;          // weight ring depth
+constexpr int NUM_THREADS = 320;   // warp 0 producer, warp 1 MMA + TMEM owner, warps 2-5 slot 0, warps 6-9 slot 1
+
+// weight blocks (16 KB each: 128 output rows x 64 K) per step, in consumption order (chunk-major, half-minor)
+__host__ __device__ constexpr int step_kchunks(int s) { return s == 0 ? 1 : (s == 5 || s == 9) ? 5 : 4; }
+__host__ __device__ constexpr int step_halves(int s) { return s == 9 ? 1 : 2; }
+__host__ __device__ constexpr int step_block0(int s) {
+  int b = 0;
+  for (int i = 0; i < s; ++i) b += step_kchunks(i) * step_halves(i);
+  return b;
+}
+constexpr int TOTAL_BLOCKS = step_block0(NSTEP);   // 2 + 32 + 10 + 16 + 8 + 5 = 73
+static_assert(TOTAL_BLOCKS == 73, "weight block count");
+
+// shared memory map (offsets from a 1024-byte aligned base)
+constexpr int SM_ACT = 0;                                   // [2 slots][4 chunks][16 KB]
+constexpr int SM_PE = SM_ACT + 2 * 4 * CHUNK_BYTES;         // [2 slots][16 KB]
+constexpr int SM_W = SM_PE + 2 * CHUNK_BYTES;               // [NSTAGE][16 KB]
+constexpr int SM_BAR = SM_W + NSTAGE * CHUNK_BYTES;         // barriers + tmem pointer
+constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;                 // slack for manual 1024-byte alignment
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+// fp32 side parameters (biases and the two small heads evaluated on CUDA cores), device resident
+struct MlpSide {
+  float bias[8][W_];       // pts_linears.0..7
+  float bias_feat[W_];
+  float bias_views[128];
+  float w_alpha[W_];
+  float w_rgb[3][128];
+  float b_alpha;
+  float b_rgb[3];
+};
+
+}  // namespace nfb
+
+struct nfb_mlp {
+  __nv_bfloat16* image;      // TOTAL_BLOCKS x 16 KB pre-swizzled weight blocks
+  nfb::MlpSide* side;
+  int* abort_flag;           // set by the kernel if a barrier wait timed out
+  int device;
+  int64_t n_params;
+};
+
+namespace nfb {
+
+// state_dict offsets in the flat fp32 parameter buffer (nn.Module registration order, run_nerf_helpers.py:82-96)
+struct ParamLayout {
+  int64_t w_pts[8], b_pts[8], w_views, b_views, w_feat, b_feat, w_alpha, b_alpha, w_rgb, b_rgb, total;
+};
+__host__ __device__ inline ParamLayout param_layout() {
+  ParamLayout p{};
+  int64_t o = 0;
+  for (int l = 0; l < 8; ++l) {
+    const int in = (l == 0) ? CH_PTS : (l == 5 ? W_ + CH_PTS : W_);
+    p.w_pts[l] = o; o += (int64_t)W_ * in;
+    p.b_pts[l] = o; o += W_;
+  }
+  p.w_views = o; o += 128 * (W_ + CH_DIR);
+  p.b_views = o; o += 128;
+  p.w_feat = o; o += W_ * W_;
+  p.b_feat = o; o += W_;
+  p.w_alpha = o; o += W_;
+  p.b_alpha = o; o += 1;
+  p.w_rgb = o; o += 3 * 128;
+  p.b_rgb = o; o += 3;
+  p.total = o;
+  return p;
+}
+
+// byte offset of element (row, k) inside a 128x64 bf16 K-major chunk with the 128-byte swizzle
+// (16-byte unit index XOR row%8; chunk base must be 1024-byte aligned) — the layout both the UMMA smem
+// descriptors below and the epilogue's manual stores use.
+__host__ __device__ __forceinline__ int swz_off(int row, int k) {
+  return row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + ((k & 7) << 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing: fp32 state_dict -> bf16 swizzled blocks + fp32 side parameters
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ image,
+                                    MlpSide* __restrict__ side) {
+  const ParamLayout pl = param_layout();
+  // one thread per bf16 element of the image
+  const int64_t total = (int64_t)TOTAL_BLOCKS * TILE_M * KCH;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int blk = (int)(e / (TILE_M * KCH));
+    const int within = (int)(e % (TILE_M * KCH));
+    const int nrow = within / KCH, kk = within % KCH;
+    int s = 0;
+    while (s + 1 < NSTEP && step_block0(s + 1) <= blk) ++s;
+    const int local = blk - step_block0(s);
+    const int halves = step_halves(s);
+    const int chunk = local / halves, half = local % halves;
+    const int n = half * 128 + nrow;           // output feature
+    float v = 0.f;
+    if (s <= 7) {
+      const int in = (s == 0) ? CH_PTS : (s == 5 ? W_ + CH_PTS : W_);
+      int col = -1;                            // column of the reference weight [256, in]
+      if (s == 0) col = (kk < CH_PTS) ? kk : -1;
+      else if (s == 5) {                       // cat([input_pts, h]) : chunk 0 = PE part, chunks 1..4 = h part
+        if (chunk == 0) col = (kk < CH_PTS) ? kk : -1;
+        else col = CH_PTS + (chunk - 1) * KCH + kk;
+      } else col = chunk * KCH + kk;
+      if (col >= 0) v = params[pl.w_pts[s] + (int64_t)n * in + col];
+    } else if (s == 8) {
+      v = params[pl.w_feat + (int64_t)n * W_ + chunk * KCH + kk];
+    } else {                                   // views: cat([feature, input_views]) : chunks 0..3 feature, chunk 4 dirs
+      const int in = W_ + CH_DIR;
+      int col = -1;
+      if (chunk < 4) col = chunk * KCH + kk;
+      else col = (kk < CH_DIR) ? W_ + kk : -1;
+      if (col >= 0) v = params[pl.w_views + (int64_t)n * in + col];
+    }
+    char* dst = reinterpret_cast<char*>(image) + (int64_t)blk * CHUNK_BYTES + swz_off(nrow, kk);
+    *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v);
+  }
+  // side parameters
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nt = gridDim.x * blockDim.x;
+  for (int i = t; i < 8 * W_; i += nt) side->bias[i / W_][i % W_] = params[pl.b_pts[i / W_] + i % W_];
+  for (int i = t; i < W_; i += nt) { side->bias_feat[i] = params[pl.b_feat + i]; side->w_alpha[i] = params[pl.w_alpha + i]; }
+  for (int i = t; i < 128; i += nt) side->bias_views[i] = params[pl.b_views + i];
+  for (int i = t; i < 3 * 128; i += nt) side->w_rgb[i / 128][i % 128] = params[pl.w_rgb + i];
+  if (t == 0) {
+    side->b_alpha = params[pl.b_alpha];
+    side->b_rgb[0] = params[pl.b_rgb]; side->b_rgb[1] = params[pl.b_rgb + 1]; side->b_rgb[2] = params[pl.b_rgb + 2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  On timeout the abort flag is raised, every later wait
+// in the grid falls through, the kernel finishes with garbage and the host reports NFB_E_CUDA.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22) || ((spins & 1023u) == 0 && *abort_flag)) { *abort_flag = 1; break; }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address        bits [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset  bits [16,30) (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                            // version = 1 (sm_100) bits [46,48)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B         bits [61,64)
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// positional encoding of one 3-vector into `feat` (bf16 pairs), reference order [x, sin(2^0 x), cos(2^0 x), ...]
+// sin/cos of 2^l x by exact angle doubling from an accurate sincosf(x): the error doubles per octave and stays
+// below 3e-5 at l = 9, two orders under the bf16 rounding that follows.
+// ---------------------------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void encode3(float x, float y, float z, float (&f)[64]) {
+  f[0] = x; f[1] = y; f[2] = z;
+  float s[3], c[3];
+  sincosf(x, &s[0], &c[0]); sincosf(y, &s[1], &c[1]); sincosf(z, &s[2], &c[2]);
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      f[3 + 6 * l + a] = s[a];
+      f[3 + 6 * l + 3 + a] = c[a];
+      const float s2 = 2.f * s[a] * c[a];
+      const float c2 = 1.f - 2.f * s[a] * s[a];
+      s[a] = s2; c[a] = c2;
+    }
+  }
+#pragma unroll
+  for (int i = 3 + 6 * L; i < 64; ++i) f[i] = 0.f;
+}
+
+__device__ __forceinline__ void store_row_chunk(uint32_t chunk_base, int row, const float (&f)[64]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint32_t addr = chunk_base + row * 128 + (((u ^ (row & 7)) & 7) << 4);
+    st_shared_v4(addr, pack_bf16(f[8 * u], f[8 * u + 1]), pack_bf16(f[8 * u + 2], f[8 * u + 3]),
+                 pack_bf16(f[8 * u + 4], f[8 * u + 5]), pack_bf16(f[8 * u + 6], f[8 * u + 7]));
+  }
+}
+
+struct FwdArgs {
+  const __nv_bfloat16* image;
+  const MlpSide* side;
+  int* abort_flag;
+  int mode;                 // 0: explicit pts + dirs, 1: rays + z_vals
+  const float* pts;         // [M,3]
+  const float* dirs;        // [R,3]
+  const float* rays;        // [R,11]
+  const float* z_vals;      // [M]
+  int64_t M;                // R*S samples
+  int S;
+  float* raw;               // [M,4]
+  int nsteps;               // 10 normally; < 10 = debug: stop after that many MMA steps and dump activations
+  float* dbg;               // [M,256] fp32 post-activation values of the last executed step (debug only)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mlp_fused_fwd_kernel(const FwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = base + SM_BAR;
+  // barrier map (8 bytes each)
+  auto W_FULL = [&](int s) { return bar0 + 8 * s; };
+  auto W_EMPTY = [&](int s) { return bar0 + 8 * (NSTAGE + s); };
+  auto A_READY = [&](int g) { return bar0 + 8 * (2 * NSTAGE + g); };
+  auto ACC_FULL = [&](int g) { return bar0 + 8 * (2 * NSTAGE + 2 + g); };
+  const uint32_t tmem_slot = bar0 + 8 * (2 * NSTAGE + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + SM_BAR + 8 * (2 * NSTAGE + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  volatile int* abort_flag = a.abort_flag;
+  const int nsteps = a.nsteps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(A_READY(g), 128); mbar_init(ACC_FULL(g), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {   // TMEM: all 512 columns (two 128x256 fp32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int64_t ntiles = (a.M + TILE_M - 1) / TILE_M;
+  const int64_t npairs = (ntiles + 1) / 2;
+
+  if (warp == 0) {
+    // ================= weight producer =================
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      for (int s = 0; s < nsteps; ++s) {
+        const int nblk = step_kchunks(s) * step_halves(s);
+        const char* src = reinterpret_cast<const char*>(a.image) + (int64_t)step_block0(s) * CHUNK_BYTES;
+        for (int g = 0; g < 2; ++g) {
+          for (int b = 0; b < nblk; ++b) {
+            mbar_wait(W_EMPTY(stage), phase ^ 1, abort_flag);
+            if (lane == 0) {
+              mbar_arrive_expect_tx(W_FULL(stage), CHUNK_BYTES);
+              bulk_g2s(base + SM_W + stage * CHUNK_BYTES, src + (int64_t)b * CHUNK_BYTES, CHUNK_BYTES, W_FULL(stage));
+            }
+            __syncwarp();
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    int stage = 0; uint32_t phase = 0;
+    uint32_t ready_phase[2] = {0, 0};
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      for (int s = 0; s < nsteps; ++s) {
+        const int kch = step_kchunks(s), halves = step_halves(s);
+        const uint32_t idesc = umma_idesc(128);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(A_READY(g), ready_phase[g], abort_flag);
+          ready_phase[g] ^= 1;
+          tc_fence_after();
+          const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES;
+          const uint32_t pe = base + SM_PE + g * CHUNK_BYTES;
+          for (int c = 0; c < kch; ++c) {
+            // A chunk for this K range: step 0 -> PE; step 5 -> PE then h0..h3; step 9 -> f0..f3 then dir PE
+            uint32_t a_chunk;
+            if (s == 0) a_chunk = pe;
+            else if (s == 5) a_chunk = (c == 0) ? pe : act + (c - 1) * CHUNK_BYTES;
+            else if (s == 9) a_chunk = (c == 4) ? pe : act + c * CHUNK_BYTES;
+            else a_chunk = act + c * CHUNK_BYTES;
+            for (int h = 0; h < halves; ++h) {
+              mbar_wait(W_FULL(stage), phase, abort_flag);
+              tc_fence_after();
+              if (lane == 0) {
+                const uint32_t wb = base + SM_W + stage * CHUNK_BYTES;
+                const uint32_t d = tmem_base + g * 256 + h * 128;
+#pragma unroll
+                for (int k = 0; k < KCH / 16; ++k) {
+                  umma_bf16(d, umma_desc(a_chunk + k * 32), umma_desc(wb + k * 32), idesc, (c > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(W_EMPTY(stage));                       // frees the weight slot when these MMAs retire
+                if (c == kch - 1 && h == halves - 1) umma_commit(ACC_FULL(g));
+              }
+              __syncwarp();
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ================= input stage + epilogues (one thread = one sample = one TMEM lane) =================
+    const int g = (warp - 2) >> 2;                    // slot
+    const int row = ((warp & 3) << 5) + lane;         // TMEM lane quarter is fixed by warp id % 4
+    const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES;
+    const uint32_t pe = base + SM_PE + g * CHUNK_BYTES;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) << 5) << 16) + g * 256;
+    const MlpSide* __restrict__ sd = a.side;
+    uint32_t full_phase = 0;
+    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+      const int64_t m = (pair * 2 + g) * TILE_M + row;
+      const bool live = m < a.M;
+      // ---- input stage ----
+      float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+      if (live) {
+        const int64_t r = m / a.S;
+        if (a.mode == 0) {
+          px = __ldg(a.pts + m * 3); py = __ldg(a.pts + m * 3 + 1); pz = __ldg(a.pts + m * 3 + 2);
+          vx = __ldg(a.dirs + r * 3); vy = __ldg(a.dirs + r * 3 + 1); vz = __ldg(a.dirs + r * 3 + 2);
+        } else {
+          const float* ray = a.rays + r * 11;
+          const float z = __ldg(a.z_vals + m);
+          px = __fadd_rn(__ldg(ray), __fmul_rn(__ldg(ray + 3), z));        // run_nerf.py:381
+          py = __fadd_rn(__ldg(ray + 1), __fmul_rn(__ldg(ray + 4), z));
+          pz = __fadd_rn(__ldg(ray + 2), __fmul_rn(__ldg(ray + 5), z));
+          vx = __ldg(ray + 8); vy = __ldg(ray + 9); vz = __ldg(ray + 10);
+        }
+      }
+      {
+        float f[64];
+        encode3<L_PTS>(px, py, pz, f);
+        store_row_chunk(pe, row, f);
+      }
+      fence_proxy_async();
+      mbar_arrive(A_READY(g));
+
+      float sigma = 0.f;
+      for (int s = 0; s < nsteps; ++s) {
+        mbar_wait(ACC_FULL(g), full_phase, abort_flag);
+        full_phase ^= 1;
+        tc_fence_after();
+        const bool last = (s == nsteps - 1);
+        if (s < 9) {
+          const float* __restrict__ bias = (s < 8) ? sd->bias[s] : sd->bias_feat;
+          const bool relu = (s < 8);
+          float sig_acc = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {                // 64 accumulator columns = one activation K-chunk
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tmem_row + c * 64, v0);
+            tmem_ld32(tmem_row + c * 64 + 32, v1);
+            tmem_ld_wait();
+            float h[64];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 64) + q);
+              h[4 * q] = __uint_as_float(v0[4 * q]) + b4.x;
+              h[4 * q + 1] = __uint_as_float(v0[4 * q + 1]) + b4.y;
+              h[4 * q + 2] = __uint_as_float(v0[4 * q + 2]) + b4.z;
+              h[4 * q + 3] = __uint_as_float(v0[4 * q + 3]) + b4.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 64 + 32) + q);
+              h[32 + 4 * q] = __uint_as_float(v1[4 * q]) + b4.x;
+              h[32 + 4 * q + 1] = __uint_as_float(v1[4 * q + 1]) + b4.y;
+              h[32 + 4 * q + 2] = __uint_as_float(v1[4 * q + 2]) + b4.z;
+              h[32 + 4 * q + 3] = __uint_as_float(v1[4 * q + 3]) + b4.w;
+            }
+            if (s == 7) {                              // alpha_linear on the fp32 activations (run_nerf_helpers.py:110)
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(sd->w_alpha + c * 64) + q);
+                sig_acc = fmaf(fmaxf(h[4 * q], 0.f), w4.x, sig_acc);
+                sig_acc = fmaf(fmaxf(h[4 * q + 1], 0.f), w4.y, sig_acc);
+                sig_acc = fmaf(fmaxf(h[4 * q + 2], 0.f), w4.z, sig_acc);
+                sig_acc = fmaf(fmaxf(h[4 * q + 3], 0.f), w4.w, sig_acc);
+              }
+            }
+            if (last && a.dbg) {
+              if (live) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  float4 o = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+                  if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                  reinterpret_cast<float4*>(a.dbg + m * 256 + c * 64)[q] = o;
+                }
+              }
+            } else {
+              const uint32_t cb = act + c * CHUNK_BYTES;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const uint32_t addr = cb + row * 128 + (((u ^ (row & 7)) & 7) << 4);
+                if (relu)
+                  st_shared_v4(addr, pack_bf16_relu(h[8 * u], h[8 * u + 1]), pack_bf16_relu(h[8 * u + 2], h[8 * u + 3]),
+                               pack_bf16_relu(h[8 * u + 4], h[8 * u + 5]), pack_bf16_relu(h[8 * u + 6], h[8 * u + 7]));
+                else
+                  st_shared_v4(addr, pack_bf16(h[8 * u], h[8 * u + 1]), pack_bf16(h[8 * u + 2], h[8 * u + 3]),
+                               pack_bf16(h[8 * u + 4], h[8 * u + 5]), pack_bf16(h[8 * u + 6], h[8 * u + 7]));
+              }
+            }
+          }
+          if (s == 7) sigma = sig_acc + __ldg(&sd->b_alpha);
+          if (s == 8) {                                // the PE chunk is free since step 5 retired: view-direction features
+            float f[64];
+            encode3<L_DIR>(vx, vy, vz, f);
+            store_row_chunk(pe, row, f);
+          }
+          if (!last) {
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(A_READY(g));
+          }
+        } else {
+          // ---- views layer epilogue: relu(acc + b) . w_rgb -> raw ----
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {                // 32 columns at a time
+            uint32_t v0[32];
+            tmem_ld32(tmem_row + c * 32, v0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(sd->bias_views + c * 32) + q);
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[0] + c * 32) + q);
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[1] + c * 32) + q);
+              const float4 w2 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[2] + c * 32) + q);
+              const float h0 = fmaxf(__uint_as_float(v0[4 * q]) + b4.x, 0.f);
+              const float h1 = fmaxf(__uint_as_float(v0[4 * q + 1]) + b4.y, 0.f);
+              const float h2 = fmaxf(__uint_as_float(v0[4 * q + 2]) + b4.z, 0.f);
+              const float h3 = fmaxf(__uint_as_float(v0[4 * q + 3]) + b4.w, 0.f);
+              r0 = fmaf(h0, w0.x, r0); r0 = fmaf(h1, w0.y, r0); r0 = fmaf(h2, w0.z, r0); r0 = fmaf(h3, w0.w, r0);
+              r1 = fmaf(h0, w1.x, r1); r1 = fmaf(h1, w1.y, r1); r1 = fmaf(h2, w1.z, r1); r1 = fmaf(h3, w1.w, r1);
+              r2 = fmaf(h0, w2.x, r2); r2 = fmaf(h1, w2.y, r2); r2 = fmaf(h2, w2.z, r2); r2 = fmaf(h3, w2.w, r2);
+              if (a.dbg && live) {
+                reinterpret_cast<float4*>(a.dbg + m * 256 + c * 32)[q] = make_float4(h0, h1, h2, h3);
+              }
+            }
+          }
+          if (live) {
+            const float4 o = make_float4(r0 + __ldg(&sd->b_rgb[0]), r1 + __ldg(&sd->b_rgb[1]), r2 + __ldg(&sd->b_rgb[2]), sigma);
+            st_stream4(reinterpret_cast<float4*>(a.raw) + m, o);
+          }
+        }
+      }
+      // the accumulator has been drained (tcgen05.wait::ld above); order it before the next tile's MMAs
+      tc_fence_before();
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+}  // namespace nfb
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_views, int skip) {
+  NFB_REQUIRE(out, "mlp_create: null out");
+  if (D != 8 || W != nfb::W_ || input_ch != nfb::CH_PTS || input_ch_views != nfb::CH_DIR || skip != 4)
+    return nfb::fail(NFB_E_UNSUPPORTED,
+                     "mlp_create: fused kernel is built for D=8 W=256 input_ch=63 input_ch_views=27 skips=[4] "
+                     "(got D=%d W=%d input_ch=%d input_ch_views=%d skip=%d)", D, W, input_ch, input_ch_views, skip);
+  nfb_mlp* h = new nfb_mlp();
+  h->image = nullptr; h->side = nullptr; h->abort_flag = nullptr;
+  h->n_params = nfb::param_layout().total;
+  cudaError_t e = cudaGetDevice(&h->device);
+  if (e == cudaSuccess) e = cudaMalloc(&h->image, (size_t)nfb::TOTAL_BLOCKS * nfb::CHUNK_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc(&h->side, sizeof(nfb::MlpSide));
+  if (e == cudaSuccess) e = cudaMalloc(&h->abort_flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->abort_flag, 0, sizeof(int));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+  if (e != cudaSuccess) {
+    cudaFree(h->image); cudaFree(h->side); cudaFree(h->abort_flag);
+    delete h;
+    return nfb::fail(NFB_E_CUDA, "mlp_create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return NFB_OK;
+}
+
+int64_t nfb_mlp_param_count(const nfb_mlp_t* h) { return h ? h->n_params : nfb::param_layout().total; }
+
+int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* stream) {
+  NFB_REQUIRE(h && params, "mlp_update: null pointer");
+  NFB_REQUIRE(n_params == h->n_params, "mlp_update: expected %lld parameters, got %lld", (long long)h->n_params, (long long)n_params);
+  nfb::pack_weights_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image, h->side);
+  return nfb::check_launch("mlp_update");
+}
+
+int nfb_mlp_destroy(nfb_mlp_t* h) {
+  if (!h) return NFB_OK;
+  cudaFree(h->image); cudaFree(h->side); cudaFree(h->abort_flag);
+  delete h;
+  return NFB_OK;
+}
+
+// 0 = healthy; 1 = a barrier wait inside the fused kernel timed out (results invalid).  Synchronises the device.
+int nfb_mlp_status(nfb_mlp_t* h) {
+  NFB_REQUIRE(h, "mlp_status: null handle");
+  int flag = 0;
+  NFB_CUDA(cudaMemcpy(&flag, h->abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(h->abort_flag, 0, sizeof(int));
+    return nfb::fail(NFB_E_CUDA, "mlp_fwd: pipeline barrier timed out inside the fused kernel");
+  }
+  return NFB_OK;
+}
+
+static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs, const float* rays,
+                      const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg, void* stream) {
+  NFB_REQUIRE(h && raw, "mlp_fwd: null handle or output");
+  NFB_REQUIRE(R >= 0 && S > 0, "mlp_fwd: R=%d S=%d", R, S);
+  NFB_REQUIRE(mode == 0 ? (pts && dirs) : (mode == 1 && rays && z_vals), "mlp_fwd: inputs missing for mode %d", mode);
+  NFB_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "mlp_fwd: raw must be 16-byte aligned");
+  NFB_REQUIRE(nsteps >= 1 && nsteps <= nfb::NSTEP && (nsteps == nfb::NSTEP || dbg), "mlp_fwd: bad nsteps");
+  if (R == 0) return NFB_OK;
+  nfb::FwdArgs a;
+  a.image = h->image; a.side = h->side; a.abort_flag = h->abort_flag;
+  a.mode = mode; a.pts = pts; a.dirs = dirs; a.rays = rays; a.z_vals = z_vals;
+  a.M = (int64_t)R * S; a.S = S; a.raw = raw; a.nsteps = nsteps; a.dbg = dbg;
+  const int64_t ntiles = (a.M + nfb::TILE_M - 1) / nfb::TILE_M;
+  const int64_t npairs = (ntiles + 1) / 2;
+  int grid = nfb::sm_count();
+  if (npairs < grid) grid = (int)npairs;
+  nfb::mlp_fused_fwd_kernel<<<grid, nfb::NUM_THREADS, nfb::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  return nfb::check_launch("mlp_fwd");
+}
+
+int nfb_mlp_fwd(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs,
+                const float* rays, const float* z_vals, int R, int S, float* raw, void* stream) {
+  return mlp_launch(h, mode, pts, dirs, rays, z_vals, R, S, raw, nfb::NSTEP, nullptr, stream);
+}
+
+// Debug/validation entry: run only the first `nsteps` MMA steps and dump the fp32 post-activation values of
+// the last one to dbg [R*S,256] (first 128 columns for the view layer).  raw is written only when nsteps == 10.
+int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs,
+                      const float* rays, const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg,
+                      void* stream) {
+  return mlp_launch(h, mode, pts, dirs, rays, z_vals, R, S, raw, nsteps, dbg, stream);
+}
+
+}  // extern "C"

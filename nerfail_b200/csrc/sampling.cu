@@ -1,0 +1,239 @@
+// Ray generation, coarse depths, inverse-CDF sampling and the fused hierarchical step.
+//
+// Reference arithmetic:
+//   get_rays        Create_spatial_point_set/nerf_pytorch/run_nerf_helpers.py:157-166, run_nerf.py:102-123
+//   coarse depths   run_nerf.py:357-379
+//   sample_pdf      run_nerf_helpers.py:200-243
+//   hierarchical    run_nerf.py:392-396, :412
+// All of these are HBM-bound and tiny next to the MLP (1 524 B/ray); the point of the
+// kernels is that the CDF, the binary search and the 192-way sort live in shared memory per ray instead
+// of the reference's expanded [R,128,63] gathers and a global sort.
+#include "common.cuh"
+
+namespace nfb {
+
+// torch.linspace(0, 1, n)[i] in fp32 (ATen's symmetric formula: forward from 0 below the midpoint,
+// backward from 1 above it).
+__device__ __forceinline__ float linspace01(int i, int n) {
+  if (n <= 1) return 0.f;
+  const float step = 1.f / (float)(n - 1);
+  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.f, __fmul_rn(step, (float)(n - 1 - i)));
+}
+
+__global__ void get_rays_kernel(int H, int W, float fx, float fy, float cx, float cy,
+                                float r00, float r01, float r02, float r10, float r11, float r12,
+                                float r20, float r21, float r22, float tx, float ty, float tz,
+                                float near_, float far_, float* __restrict__ rays) {
+  const int64_t n = (int64_t)H * W;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(p % W), j = (int)(p / W);
+    const float a = __fdiv_rn(__fsub_rn((float)i, cx), fx);
+    const float b = -__fdiv_rn(__fsub_rn((float)j, cy), fy);
+    const float c = -1.f;
+    // sum(dirs * c2w[:3,:3], -1): products then left-to-right adds, no contraction
+    const float d0 = __fadd_rn(__fadd_rn(__fmul_rn(a, r00), __fmul_rn(b, r01)), __fmul_rn(c, r02));
+    const float d1 = __fadd_rn(__fadd_rn(__fmul_rn(a, r10), __fmul_rn(b, r11)), __fmul_rn(c, r12));
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(a, r20), __fmul_rn(b, r21)), __fmul_rn(c, r22));
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+    float* o = rays + p * 11;
+    o[0] = tx; o[1] = ty; o[2] = tz;
+    o[3] = d0; o[4] = d1; o[5] = d2;
+    o[6] = near_; o[7] = far_;
+    o[8] = __fdiv_rn(d0, nrm); o[9] = __fdiv_rn(d1, nrm); o[10] = __fdiv_rn(d2, nrm);
+  }
+}
+
+__device__ __forceinline__ float coarse_depth(float near_, float far_, int i, int S, int lindisp) {
+  const float t = linspace01(i, S);
+  const float omt = __fsub_rn(1.f, t);
+  if (!lindisp) return __fadd_rn(__fmul_rn(near_, omt), __fmul_rn(far_, t));
+  return __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, near_), omt), __fmul_rn(__fdiv_rn(1.f, far_), t)));
+}
+
+__global__ void coarse_z_kernel(const float* __restrict__ rays, int R, int S, int lindisp,
+                                const float* __restrict__ t_rand, float* __restrict__ z_vals) {
+  const int64_t n = (int64_t)R * S;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(p / S), i = (int)(p % S);
+    const float near_ = __ldg(rays + (int64_t)r * 11 + 6), far_ = __ldg(rays + (int64_t)r * 11 + 7);
+    float zc = coarse_depth(near_, far_, i, S, lindisp);
+    if (t_rand) {   // run_nerf.py:365-379
+      const float zl = (i > 0) ? coarse_depth(near_, far_, i - 1, S, lindisp) : zc;
+      const float zu = (i + 1 < S) ? coarse_depth(near_, far_, i + 1, S, lindisp) : zc;
+      const float lower = (i > 0) ? __fmul_rn(0.5f, __fadd_rn(zc, zl)) : zc;
+      const float upper = (i + 1 < S) ? __fmul_rn(0.5f, __fadd_rn(zu, zc)) : zc;
+      zc = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(t_rand + p)));
+    }
+    z_vals[p] = zc;
+  }
+}
+
+// Builds the CDF of run_nerf_helpers.py:202-205 for one ray into shared memory.
+// w = weights + 1e-5; pdf = w / sum(w); cdf = [0, cumsum(pdf)] — the cumulative sum runs sequentially in
+// double and is rounded to fp32 per element, which is what ATen's CPU cumsum does for float tensors.
+__device__ __forceinline__ void build_cdf(const float* __restrict__ w, int nw, float* cdf, int lane) {
+  float part = 0.f;
+  for (int i = lane; i < nw; i += 32) part += __fadd_rn(__ldg(w + i), 1e-5f);
+  const float total = warp_sum(part);
+  for (int i = lane; i < nw; i += 32) cdf[i + 1] = __fdiv_rn(__fadd_rn(__ldg(w + i), 1e-5f), total);
+  __syncwarp();
+  if (lane == 0) {
+    double run = 0.0;
+    cdf[0] = 0.f;
+    for (int i = 1; i <= nw; ++i) { run += (double)cdf[i]; cdf[i] = (float)run; }
+  }
+  __syncwarp();
+}
+
+// torch.searchsorted(cdf, u, right=True) then the gather / lerp of :227-241.
+__device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins, int nb, float u, int* ind_out) {
+  int lo = 0, hi = nb;                 // first index with cdf[idx] > u
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  if (ind_out) *ind_out = lo;
+  const int below = max(0, lo - 1), above = min(nb - 1, lo);
+  const float c0 = cdf[below], c1 = cdf[above];
+  float denom = __fsub_rn(c1, c0);
+  if (denom < 1e-5f) denom = 1.f;
+  const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
+  const float b0 = bins[below], b1 = bins[above];
+  return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+}
+
+// dynamic smem: per warp 2*nb floats
+__global__ void __launch_bounds__(128)
+sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, int w_pitch,
+                  const float* __restrict__ u, int R, int nb, int N, float* __restrict__ samples,
+                  int32_t* __restrict__ inds) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* cdf = smem + (size_t)wib * 2 * nb;
+  float* sb = cdf + nb;
+  for (int r = blockIdx.x * wpb + wib; r < R; r += gridDim.x * wpb) {
+    for (int i = lane; i < nb; i += 32) sb[i] = __ldg(bins + (int64_t)r * nb + i);
+    build_cdf(weights + (int64_t)r * w_pitch, nb - 1, cdf, lane);
+    for (int k = lane; k < N; k += 32) {
+      const float uk = u ? __ldg(u + (int64_t)r * N + k) : linspace01(k, N);
+      int ind;
+      const float s = invert_cdf(cdf, sb, nb, uk, &ind);
+      samples[(int64_t)r * N + k] = s;
+      if (inds) inds[(int64_t)r * N + k] = ind;
+    }
+    __syncwarp();
+  }
+}
+
+// dynamic smem per warp: 2*(Sc-1) floats (cdf, bins) + P floats (sort buffer), P = pow2 >= Sc+N
+__global__ void __launch_bounds__(128)
+hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict__ weights,
+                    const float* __restrict__ u, int R, int Sc, int N, int P,
+                    float* __restrict__ z_fine, float* __restrict__ z_samples, float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int nb = Sc - 1;
+  const int per_warp = 2 * nb + P;
+  float* cdf = smem + (size_t)wib * per_warp;
+  float* sb = cdf + nb;
+  float* buf = sb + nb;
+  const int Sf = Sc + N;
+  for (int r = blockIdx.x * wpb + wib; r < R; r += gridDim.x * wpb) {
+    const float* zc = z_coarse + (int64_t)r * Sc;
+    for (int i = lane; i < Sc; i += 32) buf[i] = __ldg(zc + i);
+    for (int i = Sf + lane; i < P; i += 32) buf[i] = INFINITY;
+    __syncwarp();
+    for (int i = lane; i < nb; i += 32) sb[i] = __fmul_rn(0.5f, __fadd_rn(buf[i + 1], buf[i]));   // :392
+    build_cdf(weights + (int64_t)r * Sc + 1, nb - 1, cdf, lane);                                    // weights[...,1:-1]
+    float sum = 0.f;
+    for (int k = lane; k < N; k += 32) {
+      const float uk = u ? __ldg(u + (int64_t)r * N + k) : linspace01(k, N);
+      const float s = invert_cdf(cdf, sb, nb, uk, nullptr);
+      buf[Sc + k] = s;
+      sum += s;
+      if (z_samples) z_samples[(int64_t)r * N + k] = s;
+    }
+    if (z_std) {   // torch.std(z_samples, -1, unbiased=False)
+      __syncwarp();
+      const float mean = warp_sum(sum) / (float)N;
+      float sq = 0.f;
+      for (int k = lane; k < N; k += 32) { const float dlt = buf[Sc + k] - mean; sq += dlt * dlt; }
+      sq = warp_sum(sq);
+      if (lane == 0) z_std[r] = sqrtf(sq / (float)N);
+    }
+    __syncwarp();
+    // torch.sort(cat([z_vals, z_samples])) -> values only, so an in-smem bitonic network is equivalent
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < P; i += 32) {
+          const int l = i ^ j;
+          if (l > i) {
+            const float a = buf[i], b = buf[l];
+            const bool asc = (i & k) == 0;
+            if ((a > b) == asc) { buf[i] = b; buf[l] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (int i = lane; i < Sf; i += 32) z_fine[(int64_t)r * Sf + i] = buf[i];
+    __syncwarp();
+  }
+}
+
+static int grid_for(int64_t items, int per_block, int blocks_per_sm) {
+  int64_t blocks = (items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace nfb
+
+extern "C" {
+
+int nfb_get_rays(int H, int W, const double* K, const float* c, float near_, float far_, float* rays, void* stream) {
+  NFB_REQUIRE(H > 0 && W > 0 && K && c && rays, "get_rays: H=%d W=%d and non-null K, c2w, rays required", H, W);
+  nfb::get_rays_kernel<<<nfb::grid_for((int64_t)H * W, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      H, W, (float)K[0], (float)K[4], (float)K[2], (float)K[5],
+      c[0], c[1], c[2], c[4], c[5], c[6], c[8], c[9], c[10], c[3], c[7], c[11], near_, far_, rays);
+  return nfb::check_launch("get_rays");
+}
+
+int nfb_coarse_z(const float* rays, int R, int S, int lindisp, const float* t_rand, float* z_vals, void* stream) {
+  NFB_REQUIRE(rays && z_vals && R >= 0 && S > 0, "coarse_z: R=%d S=%d", R, S);
+  if (R == 0) return NFB_OK;
+  nfb::coarse_z_kernel<<<nfb::grid_for((int64_t)R * S, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      rays, R, S, lindisp, t_rand, z_vals);
+  return nfb::check_launch("coarse_z");
+}
+
+int nfb_sample_pdf(const float* bins, const float* weights, int w_pitch, const float* u,
+                   int R, int nb, int N, float* samples, int32_t* inds, void* stream) {
+  NFB_REQUIRE(bins && weights && samples, "sample_pdf: null pointer");
+  NFB_REQUIRE(R >= 0 && nb >= 2 && N > 0 && w_pitch >= nb - 1, "sample_pdf: R=%d nb=%d N=%d w_pitch=%d", R, nb, N, w_pitch);
+  if (nb > 2048) return nfb::fail(NFB_E_UNSUPPORTED, "sample_pdf: %d bins > 2048", nb);
+  if (R == 0) return NFB_OK;
+  const size_t smem = (size_t)4 * 2 * nb * sizeof(float);
+  nfb::sample_pdf_kernel<<<nfb::grid_for(R, 4, 16), 128, smem, (cudaStream_t)stream>>>(
+      bins, weights, w_pitch, u, R, nb, N, samples, inds);
+  return nfb::check_launch("sample_pdf");
+}
+
+int nfb_hierarchical(const float* z_coarse, const float* weights, const float* u, int R, int Sc, int N,
+                     float* z_fine, float* z_samples, float* z_std, void* stream) {
+  NFB_REQUIRE(z_coarse && weights && z_fine, "hierarchical: null pointer");
+  NFB_REQUIRE(R >= 0 && N > 0, "hierarchical: R=%d N=%d", R, N);
+  if (Sc < 3 || Sc > 128 || Sc + N > 512)
+    return nfb::fail(NFB_E_UNSUPPORTED, "hierarchical: need 3 <= Sc <= 128 and Sc+N <= 512 (Sc=%d N=%d)", Sc, N);
+  if (R == 0) return NFB_OK;
+  int P = 1;
+  while (P < Sc + N) P <<= 1;
+  const size_t smem = (size_t)4 * (2 * (Sc - 1) + P) * sizeof(float);
+  nfb::hierarchical_kernel<<<nfb::grid_for(R, 4, 16), 128, smem, (cudaStream_t)stream>>>(
+      z_coarse, weights, u, R, Sc, N, P, z_fine, z_samples, z_std);
+  return nfb::check_launch("hierarchical");
+}
+
+}  // extern "C"

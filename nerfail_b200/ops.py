@@ -1,0 +1,464 @@
+"""Tensor-level wrappers over the C ABI and the autograd.Functions built from them.
+
+Every function here launches hand-written sm_100a kernels through ctypes; PyTorch only owns the memory
+and the stream.  Reference citations (file:line, relative to the NeRFail tree) name the code each op replaces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("nerfail_b200: CUDA tensors required (the B200 kernels have no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------------------------
+# rays / depths
+# ------------------------------------------------------------------------------------------------
+def get_ray_batch(H: int, W: int, K, c2w, near: float, far: float, device=None) -> torch.Tensor:
+    """[H*W, 11] ray batch (o, d, near, far, viewdir) for one pinhole camera.
+
+    Replaces run_nerf_helpers.py:157-166 (get_rays) + run_nerf.py:102-123.
+    """
+    device = torch.device(device if device is not None else "cuda")
+    K_h = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(3, 3))
+    c2w_h = np.ascontiguousarray(
+        (c2w.detach().cpu().numpy() if isinstance(c2w, torch.Tensor) else np.asarray(c2w)).astype(np.float32)[:3, :4])
+    rays = torch.empty((H * W, 11), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(_lib.load().nfb_get_rays(H, W, K_h.ctypes.data, c2w_h.ctypes.data, float(near), float(far),
+                                       ptr(rays), stream()), "nfb_get_rays")
+    return rays
+
+
+def coarse_z(rays: torch.Tensor, n_samples: int, lindisp: bool = False, t_rand: Optional[torch.Tensor] = None):
+    """z_vals [R, n_samples] (run_nerf.py:357-379)."""
+    _require_cuda(rays, t_rand)
+    rays = _f32(rays)
+    assert rays.shape[1] >= 8
+    if rays.shape[1] != 11:
+        padded = torch.zeros((rays.shape[0], 11), dtype=torch.float32, device=rays.device)
+        padded[:, : rays.shape[1]] = rays
+        rays = padded
+    R = rays.shape[0]
+    z = torch.empty((R, n_samples), dtype=torch.float32, device=rays.device)
+    if t_rand is not None:
+        t_rand = _f32(t_rand)
+        assert t_rand.shape == (R, n_samples)
+    with torch.cuda.device(rays.device):
+        check(_lib.load().nfb_coarse_z(ptr(rays), R, n_samples, int(bool(lindisp)), ptr(t_rand), ptr(z), stream()),
+              "nfb_coarse_z")
+    return z
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+def _rays_d_view(rays_or_d: torch.Tensor):
+    """Returns (tensor, pointer to d, pitch, has_origin)."""
+    t = _f32(rays_or_d)
+    if t.shape[-1] == 3:
+        return t, t.data_ptr(), 3, False
+    assert t.shape[-1] >= 6
+    return t, t.data_ptr() + 3 * 4, t.shape[-1], True
+
+
+def composite_fwd(raw, z_vals, rays_or_d, noise=None, white_bkgd=False, want_pts_max=False):
+    """(rgb_map, disp, acc, weights, depth[, pts_max]) — run_nerf.py:262-305, nerf_to_coord.py:418-421."""
+    _require_cuda(raw, z_vals, rays_or_d, noise)
+    raw, z_vals = _f32(raw), _f32(z_vals)
+    R, S = z_vals.shape
+    assert raw.shape == (R, S, 4), f"raw {tuple(raw.shape)} vs z_vals {tuple(z_vals.shape)}"
+    keep, dptr, pitch, has_o = _rays_d_view(rays_or_d)
+    if want_pts_max and not has_o:
+        raise RuntimeError("pts_max needs the full ray batch (origins), got directions only")
+    dev = raw.device
+    rgb = torch.empty((R, 3), dtype=torch.float32, device=dev)
+    disp = torch.empty((R,), dtype=torch.float32, device=dev)
+    acc = torch.empty((R,), dtype=torch.float32, device=dev)
+    wts = torch.empty((R, S), dtype=torch.float32, device=dev)
+    depth = torch.empty((R,), dtype=torch.float32, device=dev)
+    pmax = torch.empty((R, 3), dtype=torch.float32, device=dev) if want_pts_max else None
+    noise = _f32(noise) if noise is not None else None
+    with torch.cuda.device(dev):
+        check(_lib.load().nfb_composite_fwd(ptr(raw), ptr(z_vals), dptr, pitch, ptr(noise), R, S, int(bool(white_bkgd)),
+                                            ptr(rgb), ptr(disp), ptr(acc), ptr(wts), ptr(depth), ptr(pmax), stream()),
+              "nfb_composite_fwd")
+    del keep
+    return (rgb, disp, acc, wts, depth, pmax) if want_pts_max else (rgb, disp, acc, wts, depth)
+
+
+def composite_bwd(raw, z_vals, rays_or_d, noise, white_bkgd, g_rgb, g_disp, g_acc, g_weights, g_depth):
+    raw, z_vals = _f32(raw), _f32(z_vals)
+    R, S = z_vals.shape
+    keep, dptr, pitch, _ = _rays_d_view(rays_or_d)
+    g_raw = torch.empty_like(raw)
+    gs = [None if g is None else _f32(g) for g in (g_rgb, g_disp, g_acc, g_weights, g_depth)]
+    noise = _f32(noise) if noise is not None else None
+    with torch.cuda.device(raw.device):
+        check(_lib.load().nfb_composite_bwd(ptr(raw), ptr(z_vals), dptr, pitch, ptr(noise), R, S, int(bool(white_bkgd)),
+                                            ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(gs[3]), ptr(gs[4]), ptr(g_raw),
+                                            stream()), "nfb_composite_bwd")
+    del keep
+    return g_raw
+
+
+class CompositeFn(torch.autograd.Function):
+    """Differentiable raw2outputs: gradient flows to `raw` only (z_vals / rays are constants of the render,
+    as in the reference where z_samples is detached, run_nerf.py:394)."""
+
+    @staticmethod
+    def forward(ctx, raw, z_vals, rays_or_d, noise, white_bkgd):
+        out = composite_fwd(raw, z_vals, rays_or_d, noise, white_bkgd)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(raw, z_vals, rays_or_d, noise if noise is not None else torch.empty(0, device=raw.device))
+        ctx.has_noise = noise is not None
+        ctx.white = bool(white_bkgd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc, g_weights, g_depth):
+        raw, z_vals, rays_or_d, noise = ctx.saved_tensors
+        if all(g is None for g in (g_rgb, g_disp, g_acc, g_weights, g_depth)):
+            return None, None, None, None, None
+        g_raw = composite_bwd(raw, z_vals, rays_or_d, noise if ctx.has_noise else None, ctx.white,
+                              g_rgb, g_disp, g_acc, g_weights, g_depth)
+        return g_raw, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# hierarchical sampling
+# ------------------------------------------------------------------------------------------------
+def sample_pdf(bins, weights, n_samples, u=None, return_inds=False):
+    """run_nerf_helpers.py:200-243. u=None means det=True (linspace)."""
+    _require_cuda(bins, weights, u)
+    bins, weights = _f32(bins), _f32(weights)
+    R, nb = bins.shape
+    assert weights.shape == (R, nb - 1)
+    if u is not None:
+        u = _f32(u)
+        assert u.shape == (R, n_samples)
+    out = torch.empty((R, n_samples), dtype=torch.float32, device=bins.device)
+    inds = torch.empty((R, n_samples), dtype=torch.int32, device=bins.device) if return_inds else None
+    with torch.cuda.device(bins.device):
+        check(_lib.load().nfb_sample_pdf(ptr(bins), ptr(weights), nb - 1, ptr(u), R, nb, n_samples, ptr(out), ptr(inds),
+                                         stream()), "nfb_sample_pdf")
+    return (out, inds) if return_inds else out
+
+
+def hierarchical(z_coarse, weights, n_importance, u=None):
+    """(z_fine [R,Sc+N] ascending, z_samples [R,N], z_std [R]) — run_nerf.py:392-396, :412."""
+    _require_cuda(z_coarse, weights, u)
+    z_coarse, weights = _f32(z_coarse), _f32(weights)
+    R, Sc = z_coarse.shape
+    assert weights.shape == (R, Sc)
+    if u is not None:
+        u = _f32(u)
+        assert u.shape == (R, n_importance)
+    dev = z_coarse.device
+    z_fine = torch.empty((R, Sc + n_importance), dtype=torch.float32, device=dev)
+    z_samples = torch.empty((R, n_importance), dtype=torch.float32, device=dev)
+    z_std = torch.empty((R,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().nfb_hierarchical(ptr(z_coarse), ptr(weights), ptr(u), R, Sc, n_importance, ptr(z_fine),
+                                           ptr(z_samples), ptr(z_std), stream()), "nfb_hierarchical")
+    return z_fine, z_samples, z_std
+
+
+# ------------------------------------------------------------------------------------------------
+# fused bf16 MLP
+# ------------------------------------------------------------------------------------------------
+class FusedMLP:
+    """Owns an nfb_mlp_t handle (pre-swizzled bf16 weights) for one NeRF network."""
+
+    def __init__(self, D=8, W=256, input_ch=63, input_ch_views=27, skip=4, device=None):
+        self.device = torch.device(device if device is not None else "cuda")
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.load().nfb_mlp_create(C.byref(h), D, W, input_ch, input_ch_views, skip), "nfb_mlp_create")
+        self._h = h
+        self.n_params = int(_lib.load().nfb_mlp_param_count(h))
+
+    def update(self, flat_params: torch.Tensor) -> None:
+        flat_params = _f32(flat_params)
+        with torch.cuda.device(self.device):
+            check(_lib.load().nfb_mlp_update(self._h, ptr(flat_params), flat_params.numel(), stream()), "nfb_mlp_update")
+
+    def _run(self, mode, pts, dirs, rays, z_vals, R, S, nsteps=10, want_dbg=False):
+        raw = torch.empty((R, S, 4), dtype=torch.float32, device=self.device)
+        dbg = torch.zeros((R * S, 256), dtype=torch.float32, device=self.device) if want_dbg else None
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            if want_dbg or nsteps != 10:
+                check(lib.nfb_mlp_fwd_debug(self._h, mode, ptr(pts), ptr(dirs), ptr(rays), ptr(z_vals), R, S, ptr(raw),
+                                            nsteps, ptr(dbg), stream()), "nfb_mlp_fwd_debug")
+            else:
+                check(lib.nfb_mlp_fwd(self._h, mode, ptr(pts), ptr(dirs), ptr(rays), ptr(z_vals), R, S, ptr(raw), stream()),
+                      "nfb_mlp_fwd")
+        return (raw, dbg) if want_dbg else raw
+
+    def forward_points(self, pts: torch.Tensor, dirs: torch.Tensor, **kw):
+        """pts [R,S,3], dirs [R,3] -> raw [R,S,4]."""
+        pts, dirs = _f32(pts), _f32(dirs)
+        R, S = pts.shape[0], pts.shape[1]
+        return self._run(0, pts, dirs, None, None, R, S, **kw)
+
+    def forward_rays(self, rays: torch.Tensor, z_vals: torch.Tensor, **kw):
+        """rays [R,11], z_vals [R,S] -> raw [R,S,4] with pts = o + d*z formed in-kernel."""
+        rays, z_vals = _f32(rays), _f32(z_vals)
+        assert rays.shape[1] == 11
+        R, S = z_vals.shape
+        return self._run(1, None, None, rays, z_vals, R, S, **kw)
+
+    def status(self) -> None:
+        check(_lib.load().nfb_mlp_status(self._h), "nfb_mlp_status")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().nfb_mlp_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 layer-wise path
+# ------------------------------------------------------------------------------------------------
+def embed(x: torch.Tensor, L: int, out: torch.Tensor, col0: int, row_repeat: int = 1) -> None:
+    """Writes [x, sin(2^l x), cos(2^l x)]_l into out[:, col0:col0+3+6L] (run_nerf_helpers.py:36-50)."""
+    x = _f32(x)
+    M = out.shape[0]
+    assert out.is_contiguous() and out.dtype == torch.float32
+    assert x.shape[0] * row_repeat == M
+    with torch.cuda.device(out.device):
+        check(_lib.load().nfb_embed(ptr(x), M, L, ptr(out), out.shape[1], col0, row_repeat, stream()), "nfb_embed")
+
+
+def _view2d(t: torch.Tensor):
+    """(pointer, pitch) of a 2-D fp32 view whose rows are contiguous (column slices of a row-major buffer)."""
+    assert t.dim() == 2 and t.dtype == torch.float32 and t.is_cuda
+    assert t.shape[1] == 1 or t.stride(1) == 1, "rows must be contiguous"
+    pitch = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    return t.data_ptr(), pitch
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.type, device.index)
+    cur = _ws_cache.get(key)
+    if cur is None or cur.numel() * 4 < nbytes:
+        cur = torch.empty((max(nbytes, 1 << 20) + 3) // 4, dtype=torch.float32, device=device)
+        _ws_cache[key] = cur
+    return cur
+
+
+def linear_fwd(x, weight, bias, relu: bool, out: Optional[torch.Tensor] = None):
+    M, K = x.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    xp, ldx = _view2d(x)
+    wp, ldw = _view2d(weight)
+    yp, ldy = _view2d(out)
+    with torch.cuda.device(x.device):
+        check(_lib.load().nfb_linear_fwd(xp, ldx, wp, ldw, ptr(bias) if bias is not None else None, M, N, K, int(relu), yp, ldy,
+                                         stream()), "nfb_linear_fwd")
+    return out
+
+
+def linear_bwd_data(dy, y, relu: bool, weight, out: Optional[torch.Tensor] = None, accumulate=False):
+    M, N = dy.shape
+    K = weight.shape[1]
+    if out is None:
+        out = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    dyp, lddy = _view2d(dy)
+    yp, ldy = _view2d(y) if relu else (None, 0)
+    wp, ldw = _view2d(weight)
+    dxp, lddx = _view2d(out)
+    with torch.cuda.device(dy.device):
+        check(_lib.load().nfb_linear_bwd_data(dyp, lddy, yp, ldy, int(relu), wp, ldw, M, N, K, dxp, lddx, int(accumulate),
+                                              stream()), "nfb_linear_bwd_data")
+    return out
+
+
+def linear_bwd_weight(dy, y, relu: bool, x, want_bias=True):
+    M, N = dy.shape
+    K = x.shape[1]
+    dev = dy.device
+    dW = torch.empty((N, K), dtype=torch.float32, device=dev)
+    db = torch.empty((N,), dtype=torch.float32, device=dev) if want_bias else None
+    lib = _lib.load()
+    nbytes = int(lib.nfb_linear_bwd_weight_workspace(M, N, K))
+    ws = _workspace(nbytes, dev)
+    dyp, lddy = _view2d(dy)
+    yp, ldy = _view2d(y) if relu else (None, 0)
+    xp, ldx = _view2d(x)
+    with torch.cuda.device(dev):
+        check(lib.nfb_linear_bwd_weight(dyp, lddy, yp, ldy, int(relu), xp, ldx, M, N, K, ptr(dW), K, ptr(db), ptr(ws),
+                                        ws.numel() * 4, stream()), "nfb_linear_bwd_weight")
+    return dW, db
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) with the fp32 CUDA-core kernels (addmm + relu of run_nerf_helpers.py:104-118)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x2 = x if (x.dim() == 2 and x.stride(1) == 1) else x.contiguous()
+        w2 = weight if weight.is_contiguous() else weight.contiguous()
+        y = linear_fwd(x2, w2, bias, relu)
+        ctx.relu = bool(relu)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x2, w2, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = dy if (dy.stride(1) == 1 or dy.shape[1] == 1) else dy.contiguous()
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_bwd_data(dy, y, ctx.relu, w)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dW, db = linear_bwd_weight(dy, y, ctx.relu, x, want_bias=ctx.has_bias)
+        return dx, dW, db, None
+
+
+# ------------------------------------------------------------------------------------------------
+# GaussNet
+# ------------------------------------------------------------------------------------------------
+def knn8(query: torch.Tensor, cand: torch.Tensor):
+    """(dist [Q,8] fp32, idx [Q,8] int32): exact 8-NN, create_index_and_dist.py:126-145."""
+    _require_cuda(query, cand)
+    query, cand = _f32(query).reshape(-1, 3), _f32(cand).reshape(-1, 3)
+    Q, Cn = query.shape[0], cand.shape[0]
+    dist = torch.empty((Q, 8), dtype=torch.float32, device=query.device)
+    idx = torch.empty((Q, 8), dtype=torch.int32, device=query.device)
+    with torch.cuda.device(query.device):
+        check(_lib.load().nfb_knn8(ptr(query), Q, ptr(cand), Cn, ptr(dist), None, ptr(idx), stream()), "nfb_knn8")
+    return dist, idx
+
+
+def knn8_dist_idx(query_hw3: torch.Tensor, cand: torch.Tensor) -> torch.Tensor:
+    """The reference's on-disk layout: float32 [2,H,W,8] = cat([dist, idx]) (create_index_and_dist.py:148-151)."""
+    H, W = query_hw3.shape[0], query_hw3.shape[1]
+    q = _f32(query_hw3).reshape(-1, 3)
+    cand = _f32(cand).reshape(-1, 3)
+    out = torch.empty((2, H * W, 8), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(_lib.load().nfb_knn8(ptr(q), q.shape[0], ptr(cand), cand.shape[0], out[0].data_ptr(), out[1].data_ptr(), None,
+                                   stream()), "nfb_knn8")
+    return out.reshape(2, H, W, 8)
+
+
+def gauss_weights(dist_idx: torch.Tensor, c: float) -> torch.Tensor:
+    """[B,2,H,W,8] dist/idx -> [B,2,H,W,8] weight/idx (model/GaussNet.py:169-186)."""
+    _require_cuda(dist_idx)
+    di = _f32(dist_idx)
+    B = di.shape[0]
+    HW = di.shape[2] * di.shape[3]
+    out = torch.empty_like(di)
+    with torch.cuda.device(di.device):
+        check(_lib.load().nfb_gauss_weights(ptr(di), B, HW, float(c), ptr(out), stream()), "nfb_gauss_weights")
+    return out
+
+
+def gauss_gather_fwd(table, w_idx, ori_u8, eps, minmax=None):
+    T = table.numel() // 4
+    B = w_idx.shape[0]
+    HW = w_idx.shape[2] * w_idx.shape[3]
+    shape = (B, w_idx.shape[2], w_idx.shape[3], 4)
+    x = torch.empty(shape, dtype=torch.float32, device=table.device)
+    x_rgba = torch.empty(shape, dtype=torch.float32, device=table.device)
+    with torch.cuda.device(table.device):
+        check(_lib.load().nfb_gauss_gather_fwd(ptr(table), T, ptr(w_idx), ptr(ori_u8), B, HW,
+                                               -1.0 if eps is None else float(eps), ptr(x), ptr(x_rgba), ptr(minmax),
+                                               stream()), "nfb_gauss_gather_fwd")
+    return x, x_rgba
+
+
+def gauss_scatter_bwd(g_x, g_xrgba, x, w_idx, ori_u8, eps, table_shape):
+    T = int(np.prod(table_shape)) // 4
+    B = w_idx.shape[0]
+    HW = w_idx.shape[2] * w_idx.shape[3]
+    g_table = torch.zeros(table_shape, dtype=torch.float32, device=w_idx.device)
+    g_x = None if g_x is None else _f32(g_x)
+    g_xrgba = None if g_xrgba is None else _f32(g_xrgba)
+    with torch.cuda.device(w_idx.device):
+        check(_lib.load().nfb_gauss_scatter_bwd(ptr(g_x), ptr(g_xrgba), ptr(x), ptr(w_idx), ptr(ori_u8), B, HW,
+                                                -1.0 if eps is None else float(eps), T, ptr(g_table), stream()),
+              "nfb_gauss_scatter_bwd")
+    return g_table
+
+
+class _GaussScatterFn(torch.autograd.Function):
+    """g_table = J^T (g_x, g_xrgba).  Linear in (g_x, g_xrgba): its own backward is the gather with the same
+    masks, which keeps gauss_net usable under create_graph=True (deepfool.py:76-77)."""
+
+    @staticmethod
+    def forward(ctx, g_x, g_xrgba, x, w_idx, ori_u8, eps, table_shape):
+        ctx.save_for_backward(x, w_idx, ori_u8)
+        ctx.eps = eps
+        ctx.has = (g_x is not None, g_xrgba is not None)
+        return gauss_scatter_bwd(g_x, g_xrgba, x, w_idx, ori_u8, eps, table_shape)
+
+    @staticmethod
+    def backward(ctx, gg_table):
+        x, w_idx, ori_u8 = ctx.saved_tensors
+        # d/d(g_x) <g_table, gg> = gather(gg) ; d/d(g_xrgba) = mask-scaled gather(gg)
+        gx, _ = gauss_gather_fwd(_f32(gg_table).reshape(-1, 4), w_idx, ori_u8, None)
+        g_gx = gx if ctx.has[0] else None
+        g_gxrgba = None
+        if ctx.has[1]:
+            alpha = x[..., 3:4] / 255.0
+            pr = x[..., :3] * alpha
+            orif = ori_u8.reshape(x.shape).float()
+            keep = orif[..., 3:4] > 0
+            if ctx.eps is not None:
+                keep = keep & (pr >= -ctx.eps) & (pr <= ctx.eps)
+                pr = pr.clamp(-ctx.eps, ctx.eps)
+            v = orif[..., :3] + pr
+            keep = keep & (v >= 0) & (v <= 255)
+            rgb = torch.where(keep, gx[..., :3] * alpha + gx[..., 3:4] * x[..., :3] / 255.0, torch.zeros_like(pr))
+            g_gxrgba = torch.cat([rgb, torch.zeros_like(alpha)], -1)
+        return g_gx, g_gxrgba, None, None, None, None, None
+
+
+class GaussGatherFn(torch.autograd.Function):
+    """(x, x_rgba) = gather/composite of model/GaussNet.py:53-119; backward = warp-aggregated scatter."""
+
+    @staticmethod
+    def forward(ctx, spatial_rgb, w_idx, ori_u8, eps, minmax):
+        table = _f32(spatial_rgb).reshape(-1, 4)
+        x, x_rgba = gauss_gather_fwd(table, w_idx, ori_u8, eps, minmax)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(x, w_idx, ori_u8)
+        ctx.eps = eps
+        ctx.table_shape = tuple(spatial_rgb.shape)
+        return x, x_rgba
+
+    @staticmethod
+    def backward(ctx, g_x, g_xrgba):
+        x, w_idx, ori_u8 = ctx.saved_tensors
+        if g_x is None and g_xrgba is None:
+            return None, None, None, None, None
+        g = _GaussScatterFn.apply(g_x, g_xrgba, x, w_idx, ori_u8, ctx.eps, ctx.table_shape)
+        return g, None, None, None, None

@@ -1,0 +1,322 @@
+"""Host-side mirror of nerf-pytorch's render path with the reference's signatures.
+
+Reference: Create_spatial_point_set/nerf_pytorch/run_nerf.py (render :69, batchify_rays :54, render_rays :308,
+run_network :37, raw2outputs :262, create_nerf :178, render_path :137) and the pts_max variant in
+Create_spatial_point_set/nerf_to_coord.py:70-135, :418-423.  The Python here only sequences kernel launches
+of libnerfail_b200.so; it holds no arithmetic of its own on the hot path.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import nerf, ops
+from .nerf import NeRF, get_embedder
+
+DEBUG = False
+
+
+def batchify(fn, chunk):
+    """run_nerf.py:27-34."""
+    if chunk is None:
+        return fn
+
+    def ret(inputs):
+        return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+    return ret
+
+
+def _fusable(fn, embed_fn, embeddirs_fn) -> bool:
+    return (isinstance(fn, NeRF) and fn.fused_supported()
+            and isinstance(embed_fn, nerf.Embedder) and embed_fn.multires == 10
+            and isinstance(embeddirs_fn, nerf.Embedder) and embeddirs_fn.multires == 4
+            and nerf.mlp_precision() == "bf16" and not torch.is_grad_enabled())
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """run_nerf.py:37-51.  inputs [R,S,3], viewdirs [R,3] -> [R,S,4].
+
+    Without autograd and with the reference architecture the whole call is ONE fused kernel (encoding, both
+    concats and all 12 linear layers); otherwise the encodings are written once and the fp32 layer kernels run
+    in netchunk pieces like the reference.
+    """
+    if viewdirs is not None and _fusable(fn, embed_fn, embeddirs_fn):
+        return fn.fused().forward_points(inputs, viewdirs)
+    S = inputs.shape[-2] if inputs.dim() >= 2 else 1
+    flat = inputs.reshape(-1, inputs.shape[-1])
+    if isinstance(embed_fn, nerf.Embedder):
+        width = embed_fn.out_dim + (embeddirs_fn.out_dim if viewdirs is not None else 0)
+        embedded = torch.empty((flat.shape[0], width), dtype=torch.float32, device=flat.device)
+        embed_fn.embed(flat, embedded, 0)
+        if viewdirs is not None:
+            embeddirs_fn.embed(viewdirs.reshape(-1, 3), embedded, embed_fn.out_dim, row_repeat=S)
+    else:   # i_embed == -1: identity embedding
+        embedded = embed_fn(flat)
+        if viewdirs is not None:
+            dirs = viewdirs[:, None].expand(inputs.shape).reshape(-1, inputs.shape[-1])
+            embedded = torch.cat([embedded, embeddirs_fn(dirs)], -1)
+    outputs_flat = batchify(fn, netchunk)(embedded)
+    return outputs_flat.reshape(list(inputs.shape[:-1]) + [outputs_flat.shape[-1]])
+
+
+class NetworkQuery:
+    """The `network_query_fn` built by create_nerf (run_nerf.py:201-204) as an object, so that render_rays can
+    recognise it and hand rays + depths straight to the fused kernel (points formed in-kernel)."""
+
+    def __init__(self, embed_fn, embeddirs_fn, netchunk):
+        self.embed_fn, self.embeddirs_fn, self.netchunk = embed_fn, embeddirs_fn, netchunk
+
+    def __call__(self, inputs, viewdirs, network_fn):
+        return run_network(inputs, viewdirs, network_fn, embed_fn=self.embed_fn, embeddirs_fn=self.embeddirs_fn,
+                           netchunk=self.netchunk)
+
+    def from_rays(self, ray_batch, z_vals, network_fn):
+        """raw [R,S,4] for pts = o + d*z (run_nerf.py:381) without materialising pts when the fused path applies."""
+        if ray_batch.shape[-1] == 11 and _fusable(network_fn, self.embed_fn, self.embeddirs_fn):
+            return network_fn.fused().forward_rays(ray_batch, z_vals)
+        rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+        viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
+        return self(pts, viewdirs, network_fn)
+
+
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
+    """run_nerf.py:262-305 -> (rgb_map, disp_map, acc_map, weights, depth_map); differentiable w.r.t. raw."""
+    noise = None
+    if raw_noise_std > 0.0:
+        noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std
+        if pytest:   # the reference's deterministic hook (:288-291) draws *uniform* numbers here
+            np.random.seed(0)
+            noise = torch.tensor(np.random.rand(*list(raw[..., 3].shape)) * raw_noise_std, dtype=torch.float32,
+                                 device=raw.device)
+    if raw.requires_grad and torch.is_grad_enabled():
+        return ops.CompositeFn.apply(raw, z_vals, rays_d, noise, white_bkgd)
+    return ops.composite_fwd(raw, z_vals, rays_d, noise, white_bkgd)
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
+                with_pts_max=False):
+    """run_nerf.py:308-418 (and nerf_to_coord.py:320-433 when with_pts_max=True)."""
+    ray_batch = ray_batch.float().contiguous()
+    N_rays = ray_batch.shape[0]
+    t_rand = None
+    if perturb > 0.:
+        if pytest:
+            np.random.seed(0)
+            t_rand = torch.tensor(np.random.rand(N_rays, N_samples), dtype=torch.float32, device=ray_batch.device)
+        else:
+            t_rand = torch.rand((N_rays, N_samples), device=ray_batch.device)
+    z_vals = ops.coarse_z(ray_batch, N_samples, lindisp, t_rand)
+
+    query_rays = network_query_fn.from_rays if isinstance(network_query_fn, NetworkQuery) else None
+
+    def query(z, net):
+        if query_rays is not None:
+            return query_rays(ray_batch, z, net)
+        rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+        viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+        return network_query_fn(pts, viewdirs, net)
+
+    def composite(raw, z, want_pts_max):
+        noise = None
+        if raw_noise_std > 0.:
+            noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std
+            if pytest:
+                np.random.seed(0)
+                noise = torch.tensor(np.random.rand(*list(raw[..., 3].shape)) * raw_noise_std, dtype=torch.float32,
+                                     device=raw.device)
+        if raw.requires_grad and torch.is_grad_enabled():
+            out = ops.CompositeFn.apply(raw, z, ray_batch, noise, white_bkgd)
+            pm = None
+            if want_pts_max:
+                with torch.no_grad():
+                    pm = ops.composite_fwd(raw.detach(), z, ray_batch, noise, white_bkgd, want_pts_max=True)[5]
+            return out + (pm,)
+        out = ops.composite_fwd(raw, z, ray_batch, noise, white_bkgd, want_pts_max=want_pts_max)
+        return out if want_pts_max else out + (None,)
+
+    raw = query(z_vals, network_fn)
+    rgb_map, disp_map, acc_map, weights, depth_map, pts_max = composite(raw, z_vals, with_pts_max and N_importance <= 0)
+
+    if N_importance > 0:
+        rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
+        u = None
+        if perturb != 0.:
+            if pytest:
+                np.random.seed(0)
+                u = torch.tensor(np.random.rand(N_rays, N_importance), dtype=torch.float32, device=ray_batch.device)
+            else:
+                u = torch.rand((N_rays, N_importance), device=ray_batch.device)
+        # z_mid, sample_pdf(weights[...,1:-1]), detach, sort(cat) and z_std in one kernel (:392-396, :412)
+        z_vals, z_samples, z_std = ops.hierarchical(z_vals, weights.detach(), N_importance, u)
+        run_fn = network_fn if network_fine is None else network_fine
+        raw = query(z_vals, run_fn)
+        rgb_map, disp_map, acc_map, weights, depth_map, pts_max = composite(raw, z_vals, with_pts_max)
+
+    ret = {'rgb_map': rgb_map, 'disp_map': disp_map, 'acc_map': acc_map}
+    if with_pts_max:
+        ret['pts_max'] = pts_max
+    if retraw:
+        ret['raw'] = raw
+    if N_importance > 0:
+        ret['rgb0'] = rgb_map_0
+        ret['disp0'] = disp_map_0
+        ret['acc0'] = acc_map_0
+        ret['z_std'] = z_std
+
+    if DEBUG:
+        for k in ret:
+            if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
+                print(f"! [Numerical Error] {k} contains nan or inf.")
+    return ret
+
+
+# Rays are independent, so the `chunk` argument bounds memory only ("Does not affect final results",
+# run_nerf.py:78-79).  A B200 has room for far more than the reference's 1024*32 rays per pass and the fused
+# MLP wants thousands of 128-sample tiles per launch, so consecutive chunks are coalesced up to this many
+# rays per kernel pass unless NERFAIL_B200_STRICT_CHUNK=1 asks for the reference's literal chunking.
+MAX_RAYS_PER_PASS = int(os.environ.get("NERFAIL_B200_RAYS_PER_PASS", 1 << 18))
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """run_nerf.py:54-66."""
+    if os.environ.get("NERFAIL_B200_STRICT_CHUNK", "0") != "1" and not torch.is_grad_enabled():
+        chunk = max(chunk, MAX_RAYS_PER_PASS)
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k in ret:
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
+
+
+def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, with_pts_max=False, **kwargs):
+    """run_nerf.py:69-134.  Returns [rgb_map, disp_map, acc_map, extras]; with_pts_max=True inserts pts_max
+    before extras like nerf_to_coord.py:132-135."""
+    if c2w is not None and not ndc and c2w_staticcam is None and use_viewdirs:
+        # full-image fast path: one kernel emits the [H*W,11] batch (get_rays + viewdirs + near/far)
+        dev = c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda else torch.device("cuda")
+        rays_b = ops.get_ray_batch(H, W, K, c2w, near, far, device=dev)
+        sh = (H, W, 3)
+    else:
+        if c2w is not None:
+            rays_o, rays_d = nerf.get_rays(H, W, K, c2w)
+        else:
+            rays_o, rays_d = rays
+        viewdirs = None
+        if use_viewdirs:
+            viewdirs = rays_d
+            if c2w_staticcam is not None:
+                rays_o, rays_d = nerf.get_rays(H, W, K, c2w_staticcam)
+            viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+            viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+        sh = rays_d.shape
+        if ndc:
+            rays_o, rays_d = nerf.ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+        rays_o = torch.reshape(rays_o, [-1, 3]).float()
+        rays_d = torch.reshape(rays_d, [-1, 3]).float()
+        near_t, far_t = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+        rays_b = torch.cat([rays_o, rays_d, near_t, far_t], -1)
+        if use_viewdirs:
+            rays_b = torch.cat([rays_b, viewdirs], -1)
+        if not rays_b.is_cuda:
+            raise RuntimeError("nerfail_b200.render needs CUDA rays")
+
+    all_ret = batchify_rays(rays_b, chunk, with_pts_max=with_pts_max, **kwargs)
+    for k in all_ret:
+        k_sh = list(sh[:-1]) + list(all_ret[k].shape[1:])
+        all_ret[k] = torch.reshape(all_ret[k], k_sh)
+
+    k_extract = ['rgb_map', 'disp_map', 'acc_map'] + (['pts_max'] if with_pts_max else [])
+    ret_list = [all_ret[k] for k in k_extract]
+    ret_dict = {k: all_ret[k] for k in all_ret if k not in k_extract}
+    return ret_list + [ret_dict]
+
+
+def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
+                with_pts_max=False):
+    """run_nerf.py:137-175 / nerf_to_coord.py:138-180: render every pose, optionally saving PNG (+ pts_max .npy)."""
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    rgbs, disps, pts = [], [], []
+    for i, c2w in enumerate(render_poses):
+        t0 = time.time()
+        out = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], with_pts_max=with_pts_max, **render_kwargs)
+        rgbs.append(out[0].cpu().numpy())
+        disps.append(out[1].cpu().numpy())
+        if with_pts_max:
+            pts.append(out[3].cpu().numpy())
+        if savedir is not None:
+            import cv2
+            rgb8 = nerf.to8b(rgbs[-1])
+            cv2.imwrite(os.path.join(savedir, '{:03d}.png'.format(i)), rgb8[..., ::-1])
+            if with_pts_max:
+                np.save(os.path.join(savedir, '{:03d}.npy'.format(i)), pts[-1])
+        if DEBUG:
+            print(i, time.time() - t0)
+    rgbs, disps = np.stack(rgbs, 0), np.stack(disps, 0)
+    return (rgbs, disps, np.stack(pts, 0)) if with_pts_max else (rgbs, disps)
+
+
+def create_nerf(args, device=None):
+    """run_nerf.py:178-259: embedders, coarse/fine NeRF, Adam, checkpoint reload, render kwargs."""
+    device = torch.device(device if device is not None else "cuda")
+    embed_fn, input_ch = get_embedder(args.multires, args.i_embed)
+    input_ch_views, embeddirs_fn = 0, None
+    if args.use_viewdirs:
+        embeddirs_fn, input_ch_views = get_embedder(args.multires_views, args.i_embed)
+    output_ch = 5 if args.N_importance > 0 else 4
+    skips = [4]
+    model = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, output_ch=output_ch, skips=skips,
+                 input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(device)
+    grad_vars = list(model.parameters())
+    model_fine = None
+    if args.N_importance > 0:
+        model_fine = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, input_ch=input_ch, output_ch=output_ch,
+                          skips=skips, input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(device)
+        grad_vars += list(model_fine.parameters())
+
+    network_query_fn = NetworkQuery(embed_fn, embeddirs_fn, args.netchunk)
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+
+    start = 0
+    basedir, expname = getattr(args, 'basedir', None), getattr(args, 'expname', None)
+    ckpts = []
+    if getattr(args, 'ft_path', None) is not None and args.ft_path != 'None':
+        ckpts = [args.ft_path]
+    elif basedir is not None and expname is not None and os.path.isdir(os.path.join(basedir, expname)):
+        ckpts = [os.path.join(basedir, expname, f) for f in sorted(os.listdir(os.path.join(basedir, expname)))
+                 if 'tar' in f]
+    if len(ckpts) > 0 and not getattr(args, 'no_reload', False):
+        ckpt = torch.load(ckpts[-1], map_location=device)
+        start = ckpt['global_step']
+        optimizer.load_state_dict(ckpt['optimizer_state_dict'])
+        model.load_state_dict(ckpt['network_fn_state_dict'])
+        if model_fine is not None:
+            model_fine.load_state_dict(ckpt['network_fine_state_dict'])
+
+    render_kwargs_train = {
+        'network_query_fn': network_query_fn,
+        'perturb': args.perturb,
+        'N_importance': args.N_importance,
+        'network_fine': model_fine,
+        'N_samples': args.N_samples,
+        'network_fn': model,
+        'use_viewdirs': args.use_viewdirs,
+        'white_bkgd': args.white_bkgd,
+        'raw_noise_std': args.raw_noise_std,
+    }
+    if args.dataset_type != 'llff' or args.no_ndc:
+        render_kwargs_train['ndc'] = False
+        render_kwargs_train['lindisp'] = args.lindisp
+    render_kwargs_test = {k: render_kwargs_train[k] for k in render_kwargs_train}
+    render_kwargs_test['perturb'] = False
+    render_kwargs_test['raw_noise_std'] = 0.
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer
