@@ -6,7 +6,7 @@ Drop-in names (same signatures as the reference):
 Importing the package does not need a GPU; calling any op does (there is no CPU fallback).
 """
 from .nerf import NeRF, Embedder, get_embedder, get_rays, get_rays_np, ndc_rays, sample_pdf, img2mse, mse2psnr, to8b
-from .render import (render, render_rays, run_network, raw2outputs, batchify, batchify_rays, render_path,
+from .rendering import (render, render_rays, run_network, raw2outputs, batchify, batchify_rays, render_path,
                      create_nerf, NetworkQuery)
 from .gauss import gauss_net, create_gauss_w, knn_index_and_dist
 

@@ -191,3 +191,36 @@ def render_image(H, W, K, c2w, sd_coarse, sd_fine, near=2.0, far=6.0, chunk=1024
     rays = camera_rays(H, W, K, c2w, near, far)
     parts = [render_ray_batch(rays[i:i + chunk], sd_coarse, sd_fine, **kw) for i in range(0, rays.shape[0], chunk)]
     return {k: torch.cat([p[k] for p in parts], dim=0).reshape(H, W, *parts[0][k].shape[1:]) for k in parts[0]}
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16 emulation of the fused kernel's numerics (test infrastructure for nerfail_b200/csrc/mlp_fused.cu)
+# ---------------------------------------------------------------------------------------------
+def _bf16(t: Tensor) -> Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def nerf_mlp_bf16_emulated(sd: Dict[str, Tensor], pts: Tensor, dirs: Tensor, return_steps: bool = False):
+    """Same network as nerf_mlp (H:100-121) with the rounding points of the tcgen05 kernel: encodings, weights and
+    the activations handed from layer to layer are bf16; products are exact and sums fp32; biases, the sigma head
+    (on the un-rounded layer-7 activations) and the rgb head stay fp32.  pts [M,3], dirs [M,3] -> [M,4]."""
+    mm = lambda a, w: a.double().matmul(_bf16(w).double().t()).float()
+    e_pts = _bf16(positional_encoding(pts, 10))
+    e_dir = _bf16(positional_encoding(dirs, 4))
+    steps = []
+    h = e_pts
+    h_f32 = None
+    for i in range(8):
+        h_f32 = F.relu(mm(h, sd[f"pts_linears.{i}.weight"]) + sd[f"pts_linears.{i}.bias"])
+        steps.append(h_f32)
+        h = _bf16(h_f32)
+        if i == 4:
+            h = torch.cat([e_pts, h], dim=-1)
+    sigma = F.linear(h_f32, sd["alpha_linear.weight"], sd["alpha_linear.bias"])
+    feat_f32 = mm(h, sd["feature_linear.weight"]) + sd["feature_linear.bias"]
+    steps.append(feat_f32)
+    hv = F.relu(mm(torch.cat([_bf16(feat_f32), e_dir], dim=-1), sd["views_linears.0.weight"]) + sd["views_linears.0.bias"])
+    steps.append(hv)
+    rgb = F.linear(hv, sd["rgb_linear.weight"], sd["rgb_linear.bias"])
+    out = torch.cat([rgb, sigma], dim=-1)
+    return (out, steps) if return_steps else out

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Full GPU check for one gpurun call: parity tests per file (separate processes so a CUDA fault in one file
+# cannot poison the others), smoke, a short bench.  Logs land in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+for f in kernels mlp render; do
+  timeout 900 python -m pytest tests/test_gpu_$f.py -m gpu -q -rA --timeout 600 > gpurun_out/test_$f.log 2>&1
+  echo "test_gpu_$f exit $?" >> gpurun_out/summary.txt
+done
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" >> gpurun_out/summary.txt
+timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
+echo "bench exit $?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt
+tail -5 gpurun_out/test_kernels.log gpurun_out/test_mlp.log gpurun_out/test_render.log gpurun_out/smoke.log
+tail -c 3000 gpurun_out/bench.log

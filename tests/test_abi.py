@@ -1,0 +1,88 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol include/nerfail_b200.h
+declares, the ctypes table covers them, and the product refuses to run without CUDA (no silent fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import REPO
+
+
+def header_symbols():
+    text = open(os.path.join(REPO, "include", "nerfail_b200.h")).read()
+    return sorted(set(re.findall(r"NFB_API[^;]*?\b(nfb_\w+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from nerfail_b200 import build, _lib
+    path = build.build()
+    assert path.exists()
+    lib = ctypes.CDLL(str(path))
+    names = header_symbols()
+    assert len(names) >= 26
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    assert _lib.load().nfb_abi_version() == 1
+
+
+def test_error_reporting_without_compute():
+    from nerfail_b200 import _lib
+    lib = _lib.load()
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    rc = lib.nfb_composite_fwd(None, None, None, 3, None, 4, 8, 0, None, None, None, None, None, None, None)
+    assert rc == -1 and b"composite_fwd" in lib.nfb_last_error()
+    rc = lib.nfb_hierarchical(1, 1, None, 4, 2, 128, 1, None, None, None)
+    assert rc == -2 and b"Sc" in lib.nfb_last_error()
+    rc = lib.nfb_knn8(1, 10, 1, 3, 1, None, None, None)
+    assert rc == -1
+    h = ctypes.c_void_p()
+    rc = lib.nfb_mlp_create(ctypes.byref(h), 4, 128, 63, 27, 4)
+    assert rc == -2 and b"D=8" in lib.nfb_last_error()
+
+
+def test_no_cpu_fallback():
+    import nerfail_b200 as nb
+    from nerfail_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.composite_fwd(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        nb.NeRF(use_viewdirs=True, input_ch=63, input_ch_views=27)(torch.zeros(3, 90))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.knn8(torch.zeros(4, 3), torch.zeros(16, 3))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from nerfail_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "nerfail_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_state_dict_keys_and_param_order_match_reference_layout():
+    import nerfail_b200 as nb
+    from oracle import synth
+    net = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)
+    sd = synth.random_state_dict(0)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd)
+    assert torch.equal(net.flat_params(), synth.flat_params(sd))
+    assert net.flat_params().numel() == 595844
+    assert _count() == 595844
+
+
+def _count():
+    from nerfail_b200 import _lib
+    return int(_lib.load().nfb_mlp_param_count(None))

@@ -1,0 +1,159 @@
+"""GPU parity of the network kernels: the fused bf16 tcgen05 MLP (step by step, then end to end) and the fp32
+layer-wise path (forward and parameter gradients) against the oracle / reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import nerf_oracle as no
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+def _inputs(R, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.rand(R, S, 3, generator=g) * 6 - 3
+    dirs = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    return pts, dirs
+
+
+def _fused(sd, cuda):
+    from nerfail_b200 import ops
+    m = ops.FusedMLP(device=cuda)
+    m.update(synth.flat_params(sd).to(cuda))
+    return m
+
+
+STEP_NAMES = [f"pts_linears.{i}" for i in range(8)] + ["feature_linear", "views_linears.0"]
+
+
+@pytest.mark.parametrize("nsteps", list(range(1, 11)))
+def test_fused_mlp_step_by_step(cuda, nsteps):
+    """Runs only the first n MMA steps and compares the fp32 accumulator (+bias, activation) of the last one with
+    the bf16-rounding emulation.  Localises descriptor / swizzle / pipeline errors to a layer."""
+    sd = synth.make_non_degenerate(synth.random_state_dict(0), 0)
+    R, S = 5, 77                                   # 385 samples: three full tiles + a ragged one, odd tile count
+    pts, dirs = _inputs(R, S, 100 + nsteps)
+    m = _fused(sd, cuda)
+    raw, dbg = m.forward_points(pts.to(cuda), dirs.to(cuda), nsteps=nsteps, want_dbg=True)
+    m.status()
+    _, steps = no.nerf_mlp_bf16_emulated(sd, pts.reshape(-1, 3), dirs[:, None].expand(R, S, 3).reshape(-1, 3), True)
+    want = steps[nsteps - 1]
+    got = dbg[:, : want.shape[1]].cpu()
+    scale = float(want.abs().max())
+    err = (got - want).abs()
+    # bf16 inputs with fp32 accumulation; rounding-boundary flips of earlier activations propagate, so the bound is
+    # a fraction of the layer's scale rather than ulps
+    assert float(err.max()) < 2e-2 * scale + 1e-3, (STEP_NAMES[nsteps - 1], float(err.max()), scale)
+    assert float(err.mean()) < 2e-3 * scale + 1e-4, (STEP_NAMES[nsteps - 1], float(err.mean()), scale)
+
+
+@pytest.mark.parametrize("R,S", [(1, 1), (3, 64), (2, 192), (7, 100), (64, 64), (33, 192)])
+def test_fused_mlp_end_to_end(cuda, R, S):
+    sd = synth.make_non_degenerate(synth.random_state_dict(1), 1)
+    pts, dirs = _inputs(R, S, 7 * R + S)
+    m = _fused(sd, cuda)
+    raw = m.forward_points(pts.to(cuda), dirs.to(cuda)).cpu()
+    m.status()
+    flat_p, flat_d = pts.reshape(-1, 3), dirs[:, None].expand(R, S, 3).reshape(-1, 3)
+    emu = no.nerf_mlp_bf16_emulated(sd, flat_p, flat_d).reshape(R, S, 4)
+    ref = no.query_network(sd, pts, dirs)                      # fp32 reference arithmetic
+    scale = float(ref.abs().max()) + 1e-6
+    assert float((raw - emu).abs().max()) < 3e-2 * scale, "kernel vs bf16 emulation"
+    assert float((raw - emu).abs().mean()) < 3e-3 * scale
+    # against the fp32 reference the error is the bf16 quantisation of inputs/weights/activations
+    assert float((raw - ref).abs().mean()) < 2e-2 * scale, float((raw - ref).abs().mean())
+
+
+def test_fused_mlp_ray_mode_equals_point_mode(cuda):
+    """mode 1 forms pts = o + d*z in-kernel (run_nerf.py:381); must equal mode 0 on the same points bit for bit."""
+    sd = synth.make_non_degenerate(synth.random_state_dict(2), 2)
+    K, _ = synth.intrinsics(16, 16)
+    rays = no.camera_rays(16, 16, K, torch.tensor(synth.pose_spherical(50.0, -30.0, 4.0)[:3, :4]), 2.0, 6.0)
+    z = no.coarse_depths(rays, 64)
+    pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]
+    m = _fused(sd, cuda)
+    a = m.forward_rays(rays.to(cuda), z.to(cuda))
+    b = m.forward_points(pts.to(cuda), rays[:, 8:11].contiguous().to(cuda))
+    m.status()
+    assert torch.equal(a, b)
+
+
+def test_fused_mlp_is_deterministic_and_repacks_on_update(cuda):
+    import nerfail_b200 as nb
+    net = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
+    net.load_state_dict(synth.make_non_degenerate(synth.random_state_dict(3), 3))
+    pts, dirs = _inputs(9, 64, 5)
+    with torch.no_grad():
+        a = net.fused().forward_points(pts.to(cuda), dirs.to(cuda))
+        b = net.fused().forward_points(pts.to(cuda), dirs.to(cuda))
+        assert torch.equal(a, b)
+        net.rgb_linear.bias.add_(1.0)              # in-place update bumps the version counter -> weights re-packed
+        c = net.fused().forward_points(pts.to(cuda), dirs.to(cuda))
+    torch.testing.assert_close(c[..., :3], a[..., :3] + 1.0, rtol=0, atol=1e-5)
+    assert torch.equal(c[..., 3], a[..., 3])
+
+
+def test_fp32_mlp_forward_vs_reference_golden(cuda):
+    import nerfail_b200 as nb
+    g = golden("mlp.npz")
+    net = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
+    net.load_state_dict(synth.make_non_degenerate(synth.random_state_dict(0), 0))
+    with torch.no_grad():
+        out = net(T(g["feats"]).to(cuda)).cpu().numpy()
+    # fp32 FFMA accumulation in a different order from the CPU GEMM: 1e-4 relative to the output scale
+    assert np.abs(out - g["out"]).max() < 1e-4 * np.abs(g["out"]).max()
+
+
+def test_fp32_linear_primitives_ragged(cuda):
+    from nerfail_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    for M, N, K, relu in ((1, 1, 1, False), (130, 3, 128, False), (257, 256, 63, True), (300, 128, 283, True), (1000, 256, 319, True)):
+        x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+        xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = torch.nn.functional.linear(xr, wr, br)
+        y = torch.relu(y) if relu else y
+        cot = torch.randn(M, N, generator=g)
+        (y * cot).sum().backward()
+        xc, wc, bc = (t.to(cuda).requires_grad_(True) for t in (x, w, b))
+        yc = ops.LinearFn.apply(xc, wc, bc, relu)
+        (yc * cot.to(cuda)).sum().backward()
+        for got, want, name in ((yc, y, "y"), (xc.grad, xr.grad, "dx"), (wc.grad, wr.grad, "dW"), (bc.grad, br.grad, "db")):
+            err = float((got.detach().cpu() - want.detach()).abs().max())
+            assert err < 1e-4 * (float(want.abs().max()) + 1e-6), (M, N, K, name, err)
+
+
+def test_training_step_gradients_vs_reference_golden(cuda):
+    """BASELINE config 5 in miniature: render_rays forward + backward through both networks (fp32 path), loss =
+    mse(fine) + mse(coarse) (run_nerf.py:776-791).  Parameter gradients within 1e-3 relative of the reference's."""
+    import nerfail_b200 as nb
+    g = golden("train_step.npz")
+    nets = []
+    for seed in (0, 1):
+        n = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
+        n.load_state_dict(synth.make_non_degenerate(synth.random_state_dict(seed), seed))
+        nets.append(n)
+    e10, _ = nb.get_embedder(10)
+    e4, _ = nb.get_embedder(4)
+    query = nb.NetworkQuery(e10, e4, 1 << 16)
+    rays, target = T(g["rays"]).to(cuda), T(g["target"]).to(cuda)
+    ret = nb.render_rays(rays, nets[0], query, 64, retraw=True, perturb=0., N_importance=128, network_fine=nets[1],
+                         white_bkgd=True, raw_noise_std=0.)
+    loss = nb.img2mse(ret["rgb_map"], target) + nb.img2mse(ret["rgb0"], target)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) < 1e-4 * float(g["loss"])
+    np.testing.assert_allclose(ret["rgb_map"].detach().cpu().numpy(), g["rgb"], rtol=1e-3, atol=1e-4)
+    checked = 0
+    for tag, n in (("c", nets[0]), ("f", nets[1])):
+        for name, p in n.named_parameters():
+            key = f"{tag}.{name}"
+            gn = float(np.linalg.norm(p.grad.cpu().numpy().astype(np.float64)))
+            assert abs(gn - float(g[f"norm.{key}"])) <= 1e-3 * float(g[f"norm.{key}"]) + 1e-9, (key, gn, float(g[f"norm.{key}"]))
+            if key in g:
+                ref = g[key]
+                err = np.abs(p.grad.cpu().numpy() - ref).max()
+                assert err <= 1e-3 * np.abs(ref).max() + 1e-9, (key, err, np.abs(ref).max())
+                checked += 1
+    assert checked >= 12

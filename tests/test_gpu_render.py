@@ -1,0 +1,164 @@
+"""End-to-end GPU parity of the drop-in render()/render_rays() against the reference goldens and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import nerf_oracle as no
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+class Args:
+    """The fields create_nerf reads (run_nerf.py:178-259) with configs/lego.txt values."""
+    multires, multires_views, i_embed = 10, 4, 0
+    use_viewdirs, N_importance, N_samples = True, 128, 64
+    netdepth = netdepth_fine = 8
+    netwidth = netwidth_fine = 256
+    netchunk = 1 << 16
+    lrate, perturb, white_bkgd, raw_noise_std = 5e-4, 1.0, True, 0.0
+    dataset_type, no_ndc, lindisp = "blender", False, False
+    basedir = expname = ft_path = None
+    no_reload = True
+
+
+def make_kwargs(cuda, seeds=(0, 1)):
+    import nerfail_b200 as nb
+    kw_train, kw_test, start, grad_vars, opt = nb.create_nerf(Args(), device=cuda)
+    kw_test["network_fn"].load_state_dict(synth.make_non_degenerate(synth.random_state_dict(seeds[0]), seeds[0]))
+    kw_test["network_fine"].load_state_dict(synth.make_non_degenerate(synth.random_state_dict(seeds[1]), seeds[1]))
+    assert len(grad_vars) == 48 and start == 0
+    return kw_train, kw_test
+
+
+def psnr(a, b):
+    return -10.0 * np.log10(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2) + 1e-30)
+
+
+@pytest.fixture()
+def fp32_mode(monkeypatch):
+    monkeypatch.setenv("NERFAIL_B200_MLP", "fp32")
+
+
+def test_render_fp32_matches_reference_golden(cuda, fp32_mode):
+    """fp32 accumulate path: RGB / disparity / acc / coarse outputs within 1e-3 relative of the reference render."""
+    import nerfail_b200 as nb
+    g = golden("render.npz")
+    H, W = int(g["H"]), int(g["W"])
+    _, kw = make_kwargs(cuda)
+    with torch.no_grad():
+        rgb, disp, acc, pts_max, extras = nb.render(H, W, g["K"], chunk=64, c2w=T(g["c2w"]), near=2., far=6.,
+                                                    with_pts_max=True, retraw=True, **kw)
+    for got, key in ((rgb, "rgb"), (disp, "disp"), (acc, "acc"), (extras["rgb0"], "rgb0"), (extras["disp0"], "disp0"),
+                     (extras["acc0"], "acc0"), (extras["z_std"], "z_std")):
+        ref = g[key]
+        err = np.abs(got.cpu().numpy() - ref).max()
+        assert err <= 1e-3 * np.abs(ref).max(), (key, err)
+    np.testing.assert_allclose(extras["raw"].cpu().numpy(), g["raw"], rtol=1e-3, atol=2e-3)
+    same = (np.abs(pts_max.cpu().numpy() - g["pts_max"]).max(-1) < 1e-6).mean()
+    assert same > 0.97, f"pts_max agrees on {same:.3f} of the pixels"      # arg-max flips only between near-equal weights
+
+
+def test_render_bf16_within_psnr_budget(cuda):
+    """north_star: within 0.05 dB PSNR of the fp32 reference when the MLP runs in bf16.  No ground-truth image
+    exists for random weights, so the fp32 reference render plus N(0, sigma^2) noise at a 30 dB level plays the
+    photograph: PSNR(bf16, photo) must be within 0.05 dB of PSNR(fp32 reference, photo)."""
+    import nerfail_b200 as nb
+    g = golden("render.npz")
+    H, W = int(g["H"]), int(g["W"])
+    _, kw = make_kwargs(cuda)
+    with torch.no_grad():
+        rgb, disp, acc, extras = nb.render(H, W, g["K"], chunk=64, c2w=T(g["c2w"]), near=2., far=6., **kw)
+    kw["network_fn"].fused().status(); kw["network_fine"].fused().status()
+    rng = np.random.default_rng(0)
+    photo = g["rgb"] + rng.normal(0, 10 ** (-30 / 20), g["rgb"].shape)
+    d = psnr(g["rgb"], photo) - psnr(rgb.cpu().numpy(), photo)
+    direct = psnr(rgb.cpu().numpy(), g["rgb"])
+    print(f"bf16 vs fp32 reference: direct PSNR {direct:.2f} dB, PSNR loss at 30 dB {d:.4f} dB")
+    assert abs(d) < 0.05, d
+    assert direct > 40.0, direct
+    assert np.abs(acc.cpu().numpy() - g["acc"]).mean() < 1e-2
+
+
+def test_chunking_does_not_change_results(cuda, monkeypatch):
+    """run_nerf.py:78-79: chunk 'Does not affect final results' — literal 64-ray chunks and one coalesced pass must
+    agree bit for bit (rows of an MMA tile are independent)."""
+    import nerfail_b200 as nb
+    g = golden("render.npz")
+    H, W = int(g["H"]), int(g["W"])
+    _, kw = make_kwargs(cuda)
+    with torch.no_grad():
+        a = nb.render(H, W, g["K"], chunk=64, c2w=T(g["c2w"]), near=2., far=6., **kw)
+        monkeypatch.setenv("NERFAIL_B200_STRICT_CHUNK", "1")
+        b = nb.render(H, W, g["K"], chunk=50, c2w=T(g["c2w"]), near=2., far=6., **kw)
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)
+    assert torch.equal(a[3]["z_std"], b[3]["z_std"])
+
+
+def test_rays_argument_and_generic_query_fn(cuda, fp32_mode):
+    """render(rays=...) with a plain-lambda network_query_fn (the reference's create_nerf builds a lambda,
+    run_nerf.py:201-204) goes through run_network() and must give the same image."""
+    import nerfail_b200 as nb
+    g = golden("render.npz")
+    H, W = int(g["H"]), int(g["W"])
+    _, kw = make_kwargs(cuda)
+    e10, _ = nb.get_embedder(10)
+    e4, _ = nb.get_embedder(4)
+    kw2 = dict(kw)
+    kw2["network_query_fn"] = lambda inputs, viewdirs, fn: nb.run_network(inputs, viewdirs, fn, embed_fn=e10, embeddirs_fn=e4,
+                                                                          netchunk=4096)
+    ro, rd = T(g["rays_o"]).reshape(-1, 3).to(cuda), T(g["rays_d"]).reshape(-1, 3).to(cuda)
+    with torch.no_grad():
+        rgb, disp, acc, extras = nb.render(H, W, g["K"], chunk=100, rays=(ro, rd), near=2., far=6., **kw2)
+    assert rgb.shape == (H * W, 3)
+    assert np.abs(rgb.cpu().numpy().reshape(H, W, 3) - g["rgb"]).max() < 1e-3
+
+
+def test_stochastic_path_uses_reference_pytest_hook(cuda, fp32_mode):
+    """perturb=1, raw_noise_std=1, pytest=True: the reference re-seeds numpy before every draw
+    (run_nerf.py:374-377, :288-291; run_nerf_helpers.py:215-223), which makes the stochastic path reproducible."""
+    import nerfail_b200 as nb
+    g = golden("render_stochastic.npz")
+    _, kw = make_kwargs(cuda)
+    kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
+    kw.update(perturb=1., raw_noise_std=1.)
+    with torch.no_grad():
+        out = nb.render_rays(T(g["rays"]).to(cuda), retraw=True, pytest=True, **kw)
+    for key in ("rgb_map", "acc_map", "rgb0", "acc0", "z_std"):
+        ref = g[key]
+        err = np.abs(out[key].cpu().numpy() - ref).max()
+        assert err <= 2e-3 * max(1.0, np.abs(ref).max()), (key, err)
+
+
+def test_full_size_view_properties(cuda):
+    """BASELINE config 2 size (800x800, 64+128 samples): size-independent checks instead of a full oracle render."""
+    import nerfail_b200 as nb
+    H = W = 800
+    K, _ = synth.intrinsics(H, W)
+    c2w = torch.tensor(synth.pose_spherical(30.0, -30.0, 4.0)[:3, :4])
+    _, kw = make_kwargs(cuda)
+    with torch.no_grad():
+        rgb, disp, acc, pts_max, extras = nb.render(H, W, K, chunk=1024, c2w=c2w, near=2., far=6., with_pts_max=True, **kw)
+    kw["network_fn"].fused().status(); kw["network_fine"].fused().status()
+    assert rgb.shape == (H, W, 3) and pts_max.shape == (H, W, 3)
+    assert torch.isfinite(rgb).all() and torch.isfinite(acc).all()
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-4
+    assert float(rgb.min()) >= -1e-4 and float(rgb.max()) <= 1.0 + 1e-3          # white background: convex combination
+    # pts_max lies on its ray inside [near, far]
+    rays = no.camera_rays(H, W, K, c2w, 2.0, 6.0).to(cuda)
+    t = ((pts_max.reshape(-1, 3) - rays[:, 0:3]) * rays[:, 3:6]).sum(-1) / (rays[:, 3:6] ** 2).sum(-1)
+    assert float(t.min()) >= 2.0 - 1e-3 and float(t.max()) <= 6.0 + 1e-3
+    # 512 random pixels against the fp32 oracle (bf16 budget: mean abs error of the colour)
+    g = torch.Generator().manual_seed(0)
+    pick = torch.randperm(H * W, generator=g)[:512]
+    sd_c = synth.make_non_degenerate(synth.random_state_dict(0), 0)
+    sd_f = synth.make_non_degenerate(synth.random_state_dict(1), 1)
+    with torch.no_grad():
+        ref = no.render_ray_batch(rays[pick.to(cuda)].cpu(), sd_c, sd_f)
+    got = rgb.reshape(-1, 3)[pick.to(cuda)].cpu()
+    assert psnr(got.numpy(), ref["rgb_map"].numpy()) > 40.0
