@@ -229,8 +229,9 @@ int nfb_composite_fwd(const float* raw, const float* z_vals, const float* rays_d
                       const float* noise, int R, int S, int white_bkgd,
                       float* rgb_map, float* disp, float* acc, float* weights, float* depth,
                       float* pts_max, void* stream) {
-  NFB_REQUIRE(raw && z_vals && rays_d && weights, "composite_fwd: raw, z_vals, rays_d and weights are required");
   NFB_REQUIRE(R >= 0 && S > 0 && ray_pitch >= 3, "composite_fwd: R=%d S=%d ray_pitch=%d", R, S, ray_pitch);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(raw && z_vals && rays_d && weights, "composite_fwd: raw, z_vals, rays_d and weights are required");
   NFB_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "composite_fwd: raw must be 16-byte aligned");
   if (R == 0) return NFB_OK;
   nfb::composite_fwd_kernel<<<nfb::composite_grid(R), 256, 0, (cudaStream_t)stream>>>(
@@ -242,8 +243,9 @@ int nfb_composite_bwd(const float* raw, const float* z_vals, const float* rays_d
                       const float* noise, int R, int S, int white_bkgd,
                       const float* g_rgb, const float* g_disp, const float* g_acc,
                       const float* g_weights, const float* g_depth, float* g_raw, void* stream) {
-  NFB_REQUIRE(raw && z_vals && rays_d && g_raw, "composite_bwd: raw, z_vals, rays_d and g_raw are required");
   NFB_REQUIRE(R >= 0 && S > 0 && ray_pitch >= 3, "composite_bwd: R=%d S=%d ray_pitch=%d", R, S, ray_pitch);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(raw && z_vals && rays_d && g_raw, "composite_bwd: raw, z_vals, rays_d and g_raw are required");
   NFB_REQUIRE(((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(g_raw)) & 15) == 0,
               "composite_bwd: raw and g_raw must be 16-byte aligned");
   if (S > 1024) return nfb::fail(NFB_E_UNSUPPORTED, "composite_bwd: S=%d > 1024 samples per ray", S);

@@ -3,6 +3,7 @@
 # cannot poison the others), smoke, a short bench.  Logs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
+rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 for f in kernels mlp render; do
@@ -11,8 +12,11 @@ for f in kernels mlp render; do
 done
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit $?" >> gpurun_out/summary.txt
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
-echo "bench exit $?" >> gpurun_out/summary.txt
+if [ "${SKIP_BENCH:-0}" != "1" ]; then
+  timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
+  echo "bench exit $?" >> gpurun_out/summary.txt
+fi
 cat gpurun_out/summary.txt
-tail -5 gpurun_out/test_kernels.log gpurun_out/test_mlp.log gpurun_out/test_render.log gpurun_out/smoke.log
-tail -c 3000 gpurun_out/bench.log
+grep -hE "^(FAILED|ERROR)|passed|failed" gpurun_out/test_*.log | tail -30
+tail -n 3 gpurun_out/smoke.log
+[ -f gpurun_out/bench.log ] && tail -c 2500 gpurun_out/bench.log

@@ -65,8 +65,9 @@ def test_render_fp32_matches_reference_golden(cuda, fp32_mode):
 
 def test_render_bf16_within_psnr_budget(cuda):
     """north_star: within 0.05 dB PSNR of the fp32 reference when the MLP runs in bf16.  No ground-truth image
-    exists for random weights, so the fp32 reference render plus N(0, sigma^2) noise at a 30 dB level plays the
-    photograph: PSNR(bf16, photo) must be within 0.05 dB of PSNR(fp32 reference, photo)."""
+    exists for random weights, so the photograph is modelled as the fp32 reference render plus independent noise
+    at a 30 dB level (a typical trained-NeRF test PSNR): the expected PSNR of the bf16 render against it must be
+    within 0.05 dB of the reference render's 30 dB."""
     import nerfail_b200 as nb
     g = golden("render.npz")
     H, W = int(g["H"]), int(g["W"])
@@ -74,11 +75,13 @@ def test_render_bf16_within_psnr_budget(cuda):
     with torch.no_grad():
         rgb, disp, acc, extras = nb.render(H, W, g["K"], chunk=64, c2w=T(g["c2w"]), near=2., far=6., **kw)
     kw["network_fn"].fused().status(); kw["network_fine"].fused().status()
-    rng = np.random.default_rng(0)
-    photo = g["rgb"] + rng.normal(0, 10 ** (-30 / 20), g["rgb"].shape)
-    d = psnr(g["rgb"], photo) - psnr(rgb.cpu().numpy(), photo)
+    # expected PSNR of a render r against a photo p = ref + n (n independent noise of variance s2):
+    # E|r - p|^2 = |r - ref|^2 + s2, so the expected loss is 10 log10(1 + mse(r, ref) / s2).
+    s2 = 10 ** (-30 / 10)
+    mse = float(np.mean((rgb.cpu().numpy().astype(np.float64) - g["rgb"]) ** 2))
+    d = 10 * np.log10(1 + mse / s2)
     direct = psnr(rgb.cpu().numpy(), g["rgb"])
-    print(f"bf16 vs fp32 reference: direct PSNR {direct:.2f} dB, PSNR loss at 30 dB {d:.4f} dB")
+    print(f"bf16 vs fp32 reference: direct PSNR {direct:.2f} dB, expected PSNR loss at 30 dB {d:.4f} dB")
     assert abs(d) < 0.05, d
     assert direct > 40.0, direct
     assert np.abs(acc.cpu().numpy() - g["acc"]).mean() < 1e-2
