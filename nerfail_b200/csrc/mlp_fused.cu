@@ -19,6 +19,7 @@
 //
 // Activations never leave the SM; HBM traffic is 16 B read + 16 B written per sample.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nfb {
 
@@ -133,9 +134,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, __nv_bfloa
       const int in = (s == 0) ? CH_PTS : (s == 5 ? W_ + CH_PTS : W_);
       int col = -1;                            // column of the reference weight [256, in]
       if (s == 0) col = (kk < CH_PTS) ? kk : -1;
-      else if (s == 5) {                       // cat([input_pts, h]) : chunk 0 = PE part, chunks 1..4 = h part
-        if (chunk == 0) col = (kk < CH_PTS) ? kk : -1;
-        else col = CH_PTS + (chunk - 1) * KCH + kk;
+      else if (s == 5) {                       // cat([input_pts, h]) : chunks 0..3 = h part, chunk 4 = PE part
+        if (chunk == 4) col = (kk < CH_PTS) ? kk : -1;
+        else col = CH_PTS + chunk * KCH + kk;
       } else col = chunk * KCH + kk;
       if (col >= 0) v = params[pl.w_pts[s] + (int64_t)n * in + col];
     } else if (s == 8) {
@@ -305,15 +306,72 @@ struct FwdArgs {
   float* dbg;               // [M,256] fp32 post-activation values of the last executed step (debug only)
 };
 
+// ---- cluster / cta_group::2 helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      :: "r"(bar), "r"(cta) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_issue(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+// tcgen05.commit: the mbarrier (same offset in every CTA of the group) is arrived on when all MMAs issued so far retire
+template <int CG>
+__device__ __forceinline__ void umma_commit_group(uint32_t bar) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t umma_idesc_mn(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// A-operand chunk of MMA step s, K-chunk c (consumption order: the 256-wide activation first, then the encoding chunk)
+__device__ __forceinline__ uint32_t a_chunk_addr(int s, int c, uint32_t act, uint32_t pe) {
+  if (s == 0) return pe;
+  if ((s == 5 || s == 9) && c == 4) return pe;
+  return act + c * CHUNK_BYTES;
+}
+
 // ---------------------------------------------------------------------------------------------------
-// the kernel
+// the kernel.  CG = 1: one CTA per SM, 128-row tiles, every CTA streams whole weight blocks per tile slot.
+//              CG = 2: CTA pairs (cluster of 2) run tcgen05.mma.cta_group::2 on 256-row tiles: each CTA holds its 128
+//                      rows of A and HALF of each weight block (N split), so L2->SMEM weight traffic and SMEM operand
+//                      reads per CTA are halved, one MMA covers N = 256, and both tile slots reuse the resident weights.
 // ---------------------------------------------------------------------------------------------------
+template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_fused_fwd_kernel(const FwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = base + SM_BAR;
-  // barrier map (8 bytes each)
   auto W_FULL = [&](int s) { return bar0 + 8 * s; };
   auto W_EMPTY = [&](int s) { return bar0 + 8 * (NSTAGE + s); };
   auto A_READY = [&](int g) { return bar0 + 8 * (2 * NSTAGE + g); };
@@ -322,86 +380,155 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + SM_BAR + 8 * (2 * NSTAGE + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   volatile int* abort_flag = a.abort_flag;
   const int nsteps = a.nsteps;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(A_READY(g), 128); mbar_init(ACC_FULL(g), 1); }
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(W_FULL(s), (CG == 2 && leader) ? 2 : 1);      // CG=2 leader: own producer + the peer's relay
+      mbar_init(W_EMPTY(s), 1);
+    }
+    for (int g = 0; g < 2; ++g) { mbar_init(A_READY(g), 4 * CG); mbar_init(ACC_FULL(g), 1); }
     fence_barrier_init();
   }
-  if (warp == 1) {   // TMEM: all 512 columns (two 128x256 fp32 accumulators)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // TMEM: all 512 columns (two 128x256 fp32 accumulators per CTA)
+    if constexpr (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();       // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int64_t ntiles = (a.M + TILE_M - 1) / TILE_M;
-  const int64_t npairs = (ntiles + 1) / 2;
+  constexpr int ROWS_PER_UNIT = 2 * TILE_M * CG;    // two tile slots
+  const int64_t nunits = (a.M + ROWS_PER_UNIT - 1) / ROWS_PER_UNIT;
+  const int64_t group = blockIdx.x / CG, ngroups = gridDim.x / CG;
 
   if (warp == 0) {
-    // ================= weight producer =================
-    int stage = 0; uint32_t phase = 0;
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      for (int s = 0; s < nsteps; ++s) {
-        const int nblk = step_kchunks(s) * step_halves(s);
-        const char* src = reinterpret_cast<const char*>(a.image) + (int64_t)step_block0(s) * CHUNK_BYTES;
-        for (int g = 0; g < 2; ++g) {
-          for (int b = 0; b < nblk; ++b) {
-            mbar_wait(W_EMPTY(stage), phase ^ 1, abort_flag);
-            if (lane == 0) {
-              mbar_arrive_expect_tx(W_FULL(stage), CHUNK_BYTES);
-              bulk_g2s(base + SM_W + stage * CHUNK_BYTES, src + (int64_t)b * CHUNK_BYTES, CHUNK_BYTES, W_FULL(stage));
+    // ================= weight producer (one thread) =================
+    if (lane == 0) {
+      uint32_t pos = 0;
+      for (int64_t unit = group; unit < nunits; unit += ngroups) {
+        for (int s = 0; s < nsteps; ++s) {
+          const int kch = step_kchunks(s), halves = step_halves(s);
+          const char* src = reinterpret_cast<const char*>(a.image) + (int64_t)step_block0(s) * CHUNK_BYTES;
+          if constexpr (CG == 1) {
+            for (int g = 0; g < 2; ++g)
+              for (int b = 0; b < kch * halves; ++b, ++pos) {
+                const int stage = pos & (NSTAGE - 1);
+                mbar_wait(W_EMPTY(stage), ((pos >> 2) & 1) ^ 1, abort_flag);
+                mbar_arrive_expect_tx(W_FULL(stage), CHUNK_BYTES);
+                bulk_g2s(base + SM_W + stage * CHUNK_BYTES, src + (int64_t)b * CHUNK_BYTES, CHUNK_BYTES, W_FULL(stage));
+              }
+          } else {
+            // this CTA's half of every block, once per step (both slots reuse it): N rows [rank*N/2, (rank+1)*N/2)
+            const uint32_t bytes = (halves == 2) ? CHUNK_BYTES : CHUNK_BYTES / 2;
+            for (int c = 0; c < kch; ++c, ++pos) {
+              const int stage = pos & (NSTAGE - 1);
+              const char* blk = (halves == 2) ? src + (int64_t)(c * 2 + rank) * CHUNK_BYTES
+                                              : src + (int64_t)c * CHUNK_BYTES + rank * (CHUNK_BYTES / 2);
+              mbar_wait(W_EMPTY(stage), ((pos >> 2) & 1) ^ 1, abort_flag);
+              mbar_arrive_expect_tx(W_FULL(stage), bytes);
+              bulk_g2s(base + SM_W + stage * CHUNK_BYTES, blk, bytes, W_FULL(stage));
             }
-            __syncwarp();
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    int stage = 0; uint32_t phase = 0;
-    uint32_t ready_phase[2] = {0, 0};
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      for (int s = 0; s < nsteps; ++s) {
-        const int kch = step_kchunks(s), halves = step_halves(s);
-        const uint32_t idesc = umma_idesc(128);
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(A_READY(g), ready_phase[g], abort_flag);
-          ready_phase[g] ^= 1;
-          tc_fence_after();
-          const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES;
-          const uint32_t pe = base + SM_PE + g * CHUNK_BYTES;
-          for (int c = 0; c < kch; ++c) {
-            // A chunk for this K range: step 0 -> PE; step 5 -> PE then h0..h3; step 9 -> f0..f3 then dir PE
-            uint32_t a_chunk;
-            if (s == 0) a_chunk = pe;
-            else if (s == 5) a_chunk = (c == 0) ? pe : act + (c - 1) * CHUNK_BYTES;
-            else if (s == 9) a_chunk = (c == 4) ? pe : act + c * CHUNK_BYTES;
-            else a_chunk = act + c * CHUNK_BYTES;
-            for (int h = 0; h < halves; ++h) {
-              mbar_wait(W_FULL(stage), phase, abort_flag);
+    if (lane == 0 && leader) {
+      // ================= MMA issuer (one thread) =================
+      uint32_t pos = 0;
+      uint32_t ready_phase[2] = {0, 0};
+      const uint64_t desc_hi = umma_desc(0) & 0xFFFFFFFF00000000ull;
+      auto desc_of = [&](uint32_t saddr) { return desc_hi | (uint64_t)(((saddr & 0x3FFFF) >> 4) | (1u << 16)); };
+      for (int64_t unit = group; unit < nunits; unit += ngroups) {
+        for (int s = 0; s < nsteps; ++s) {
+          const int kch = step_kchunks(s), halves = step_halves(s);
+          if constexpr (CG == 1) {
+            const uint32_t idesc = umma_idesc_mn(128, 128);
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(A_READY(g), ready_phase[g], abort_flag);
+              ready_phase[g] ^= 1;
               tc_fence_after();
-              if (lane == 0) {
-                const uint32_t wb = base + SM_W + stage * CHUNK_BYTES;
-                const uint32_t d = tmem_base + g * 256 + h * 128;
+              const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
+              for (int c = 0; c < kch; ++c) {
+                const uint64_t ad = desc_of(a_chunk_addr(s, c, act, pe));
+                for (int h = 0; h < halves; ++h, ++pos) {
+                  const int stage = pos & (NSTAGE - 1);
+                  mbar_wait(W_FULL(stage), (pos >> 2) & 1, abort_flag);
+                  tc_fence_after();
+                  const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
+                  const uint32_t d = tmem_base + g * 256 + h * 128;
 #pragma unroll
-                for (int k = 0; k < KCH / 16; ++k) {
-                  umma_bf16(d, umma_desc(a_chunk + k * 32), umma_desc(wb + k * 32), idesc, (c > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < KCH / 16; ++k)
+                    umma_issue<1>(d, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                  umma_commit_group<1>(W_EMPTY(stage));
                 }
-                umma_commit(W_EMPTY(stage));                       // frees the weight slot when these MMAs retire
-                if (c == kch - 1 && h == halves - 1) umma_commit(ACC_FULL(g));
               }
-              __syncwarp();
-              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+              umma_commit_group<1>(ACC_FULL(g));
             }
+          } else {
+            const uint32_t idesc = umma_idesc_mn(256, halves == 2 ? 256 : 128);
+            const int main_ch = kch < NSTAGE ? kch : NSTAGE;     // chunks resident together; a 5th one goes last
+            const uint32_t p0 = pos;
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(A_READY(g), ready_phase[g], abort_flag);
+              ready_phase[g] ^= 1;
+              tc_fence_after();
+              const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
+              const uint32_t d = tmem_base + g * 256;
+              for (int c = 0; c < main_ch; ++c) {
+                const uint32_t p = p0 + c;
+                const int stage = p & (NSTAGE - 1);
+                if (g == 0) { mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag); tc_fence_after(); }
+                const uint64_t ad = desc_of(a_chunk_addr(s, c, act, pe));
+                const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
+#pragma unroll
+                for (int k = 0; k < KCH / 16; ++k)
+                  umma_issue<2>(d, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                if (g == 1) umma_commit_group<2>(W_EMPTY(stage));   // both slots have consumed the block
+              }
+              if (kch == main_ch) umma_commit_group<2>(ACC_FULL(g));
+            }
+            if (kch > main_ch) {                                  // the encoding chunk of steps 5 and 9
+              const uint32_t p = p0 + main_ch;
+              const int stage = p & (NSTAGE - 1);
+              mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag);
+              tc_fence_after();
+              const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
+              for (int g = 0; g < 2; ++g) {
+                const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
+                const uint64_t ad = desc_of(a_chunk_addr(s, main_ch, act, pe));
+#pragma unroll
+                for (int k = 0; k < KCH / 16; ++k)
+                  umma_issue<2>(tmem_base + g * 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                if (g == 1) umma_commit_group<2>(W_EMPTY(stage));
+                umma_commit_group<2>(ACC_FULL(g));
+              }
+            }
+            pos += kch;
           }
         }
       }
+    } else if (CG == 2 && lane == 0 && !leader) {
+      // ================= peer relay: tells the leader when this CTA's half of a block has landed =================
+      uint32_t pos = 0;
+      for (int64_t unit = group; unit < nunits; unit += ngroups)
+        for (int s = 0; s < nsteps; ++s)
+          for (int c = 0; c < step_kchunks(s); ++c, ++pos) {
+            const int stage = pos & (NSTAGE - 1);
+            mbar_wait(W_FULL(stage), (pos >> 2) & 1, abort_flag);
+            mbar_arrive_remote(W_FULL(stage), 0);
+          }
     }
   } else {
     // ================= input stage + epilogues (one thread = one sample = one TMEM lane) =================
@@ -412,8 +539,16 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) << 5) << 16) + g * 256;
     const MlpSide* __restrict__ sd = a.side;
     uint32_t full_phase = 0;
-    for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-      const int64_t m = (pair * 2 + g) * TILE_M + row;
+    auto signal_a_ready = [&]() {                     // this warp's rows of the A operand are in shared memory
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1 || leader) mbar_arrive(A_READY(g)); else mbar_arrive_remote(A_READY(g), 0);
+      }
+    };
+    for (int64_t unit = group; unit < nunits; unit += ngroups) {
+      const int64_t m = unit * ROWS_PER_UNIT + (int64_t)g * (TILE_M * CG) + rank * TILE_M + row;
       const bool live = m < a.M;
       // ---- input stage ----
       float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
@@ -436,8 +571,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
         encode3<L_PTS>(px, py, pz, f);
         store_row_chunk(pe, row, f);
       }
-      fence_proxy_async();
-      mbar_arrive(A_READY(g));
+      signal_a_ready();
 
       float sigma = 0.f;
       for (int s = 0; s < nsteps; ++s) {
@@ -454,23 +588,21 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             uint32_t v0[32], v1[32];
             tmem_ld32(tmem_row + c * 64, v0);
             tmem_ld32(tmem_row + c * 64 + 32, v1);
+            float4 b4[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) b4[q] = __ldg(reinterpret_cast<const float4*>(bias + c * 64) + q);
             tmem_ld_wait();
             float h[64];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 64) + q);
-              h[4 * q] = __uint_as_float(v0[4 * q]) + b4.x;
-              h[4 * q + 1] = __uint_as_float(v0[4 * q + 1]) + b4.y;
-              h[4 * q + 2] = __uint_as_float(v0[4 * q + 2]) + b4.z;
-              h[4 * q + 3] = __uint_as_float(v0[4 * q + 3]) + b4.w;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 64 + 32) + q);
-              h[32 + 4 * q] = __uint_as_float(v1[4 * q]) + b4.x;
-              h[32 + 4 * q + 1] = __uint_as_float(v1[4 * q + 1]) + b4.y;
-              h[32 + 4 * q + 2] = __uint_as_float(v1[4 * q + 2]) + b4.z;
-              h[32 + 4 * q + 3] = __uint_as_float(v1[4 * q + 3]) + b4.w;
+              h[4 * q] = __uint_as_float(v0[4 * q]) + b4[q].x;
+              h[4 * q + 1] = __uint_as_float(v0[4 * q + 1]) + b4[q].y;
+              h[4 * q + 2] = __uint_as_float(v0[4 * q + 2]) + b4[q].z;
+              h[4 * q + 3] = __uint_as_float(v0[4 * q + 3]) + b4[q].w;
+              h[32 + 4 * q] = __uint_as_float(v1[4 * q]) + b4[8 + q].x;
+              h[32 + 4 * q + 1] = __uint_as_float(v1[4 * q + 1]) + b4[8 + q].y;
+              h[32 + 4 * q + 2] = __uint_as_float(v1[4 * q + 2]) + b4[8 + q].z;
+              h[32 + 4 * q + 3] = __uint_as_float(v1[4 * q + 3]) + b4[8 + q].w;
             }
             if (s == 7) {                              // alpha_linear on the fp32 activations (run_nerf_helpers.py:110)
 #pragma unroll
@@ -511,11 +643,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             encode3<L_DIR>(vx, vy, vz, f);
             store_row_chunk(pe, row, f);
           }
-          if (!last) {
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(A_READY(g));
-          }
+          if (!last) signal_a_ready();
         } else {
           // ---- views layer epilogue: relu(acc + b) . w_rgb -> raw ----
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
@@ -548,14 +676,19 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
           }
         }
       }
-      // the accumulator has been drained (tcgen05.wait::ld above); order it before the next tile's MMAs
-      tc_fence_before();
+      // the accumulator has been drained (tcgen05.wait::ld above); signal_a_ready() of the next unit orders it
     }
   }
 
+  tc_fence_before();
   __syncthreads();
+  __syncwarp();
+  if constexpr (CG == 2) cluster_sync_all();       // the peer may still be reading TMEM the leader's MMAs wrote
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512) : "memory");
+    if constexpr (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -581,7 +714,9 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
   if (e == cudaSuccess) e = cudaMalloc(&h->abort_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(h->abort_flag, 0, sizeof(int));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e != cudaSuccess) {
     cudaFree(h->image); cudaFree(h->side); cudaFree(h->abort_flag);
     delete h;
@@ -631,11 +766,27 @@ static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const floa
   a.image = h->image; a.side = h->side; a.abort_flag = h->abort_flag;
   a.mode = mode; a.pts = pts; a.dirs = dirs; a.rays = rays; a.z_vals = z_vals;
   a.M = (int64_t)R * S; a.S = S; a.raw = raw; a.nsteps = nsteps; a.dbg = dbg;
-  const int64_t ntiles = (a.M + nfb::TILE_M - 1) / nfb::TILE_M;
-  const int64_t npairs = (ntiles + 1) / 2;
-  int grid = nfb::sm_count();
-  if (npairs < grid) grid = (int)npairs;
-  nfb::mlp_fused_fwd_kernel<<<grid, nfb::NUM_THREADS, nfb::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  // NERFAIL_B200_CG=1 selects the single-CTA variant (cta_group::1); default is the CTA-pair kernel (cta_group::2).
+  static const int cg = []() { const char* e = getenv("NERFAIL_B200_CG"); return (e && e[0] == '1') ? 1 : 2; }();
+  const int64_t rows_per_unit = 2 * nfb::TILE_M * cg;
+  const int64_t nunits = (a.M + rows_per_unit - 1) / rows_per_unit;
+  int groups = nfb::sm_count() / cg;
+  if (nunits < groups) groups = (int)nunits;
+  if (cg == 1) {
+    nfb::mlp_fused_fwd_kernel<1><<<groups, nfb::NUM_THREADS, nfb::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(groups * 2));
+    cfg.blockDim = dim3(nfb::NUM_THREADS);
+    cfg.dynamicSmemBytes = nfb::SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, nfb::mlp_fused_fwd_kernel<2>, a);
+    if (e != cudaSuccess) return nfb::fail(NFB_E_CUDA, "mlp_fwd: cluster launch: %s", cudaGetErrorString(e));
+  }
   return nfb::check_launch("mlp_fwd");
 }
 

@@ -12,12 +12,12 @@
 
 namespace nfb {
 
-// torch.linspace(0, 1, n)[i] in fp32 (ATen's symmetric formula: forward from 0 below the midpoint,
-// backward from 1 above it).
+// torch.linspace(0, 1, n)[i] in fp32 exactly as ATen's CPU kernel evaluates it: step = 1/(n-1); forward from 0 below
+// the midpoint (step*i), backward from 1 above it with a FUSED multiply-subtract (1 - step*(n-1-i), one rounding).
 __device__ __forceinline__ float linspace01(int i, int n) {
   if (n <= 1) return 0.f;
-  const float step = 1.f / (float)(n - 1);
-  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.f, __fmul_rn(step, (float)(n - 1 - i)));
+  const float step = __fdiv_rn(1.f, (float)(n - 1));
+  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(n - 1 - i), 1.f);
 }
 
 __global__ void get_rays_kernel(int H, int W, float fx, float fy, float cx, float cy,
@@ -72,9 +72,14 @@ __global__ void coarse_z_kernel(const float* __restrict__ rays, int R, int S, in
 // w = weights + 1e-5; pdf = w / sum(w); cdf = [0, cumsum(pdf)] — the cumulative sum runs sequentially in
 // double and is rounded to fp32 per element, which is what ATen's CPU cumsum does for float tensors.
 __device__ __forceinline__ void build_cdf(const float* __restrict__ w, int nw, float* cdf, int lane) {
-  float part = 0.f;
-  for (int i = lane; i < nw; i += 32) part += __fadd_rn(__ldg(w + i), 1e-5f);
-  const float total = warp_sum(part);
+  // The normaliser is accumulated in double and rounded once: the correctly rounded sum is what any accurate fp32
+  // summation order (ATen's vectorised cascade on CPU, its tree on GPU) produces in the large majority of cases,
+  // which keeps the CDF — and with it the u == cdf[k] knife edges of searchsorted — aligned with the reference.
+  double part = 0.0;
+  for (int i = lane; i < nw; i += 32) part += (double)__fadd_rn(__ldg(w + i), 1e-5f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+  const float total = (float)part;
   for (int i = lane; i < nw; i += 32) cdf[i + 1] = __fdiv_rn(__fadd_rn(__ldg(w + i), 1e-5f), total);
   __syncwarp();
   if (lane == 0) {
