@@ -71,18 +71,43 @@ __global__ void coarse_z_kernel(const float* __restrict__ rays, int R, int S, in
 // Builds the CDF of run_nerf_helpers.py:202-205 for one ray into shared memory.
 // w = weights + 1e-5; pdf = w / sum(w); cdf = [0, cumsum(pdf)] — the cumulative sum runs sequentially in
 // double and is rounded to fp32 per element, which is what ATen's CPU cumsum does for float tensors.
-__device__ __forceinline__ void build_cdf(const float* __restrict__ w, int nw, float* cdf, int lane) {
-  // The normaliser is accumulated in double and rounded once: the correctly rounded sum is what any accurate fp32
-  // summation order (ATen's vectorised cascade on CPU, its tree on GPU) produces in the large majority of cases,
-  // which keeps the CDF — and with it the u == cdf[k] knife edges of searchsorted — aligned with the reference.
-  double part = 0.0;
-  for (int i = lane; i < nw; i += 32) part += (double)__fadd_rn(__ldg(w + i), 1e-5f);
+// sum(w + 1e-5) over nw contiguous floats in the exact order of ATen's CPU reduction (vectorized_inner_sum in
+// aten/src/ATen/native/cpu/SumKernel.cpp with 8-float vectors, which is what produced tests/golden): four
+// interleaved vector accumulators over groups of four 8-wide vectors, left-over vectors into accumulator 0,
+// accumulators folded 0 += 1, 2, 3, then the scalar tail summed first and the 8 lanes added to it in order.
+// Valid while every accumulator sees < 16 vectors (nw < 512); the cascade above that is not reproduced.
+// Why bother: searchsorted(cdf, u) sits on a knife edge wherever u equals a CDF knot (always for u = 1), so one ulp
+// of the normaliser moves a sample across a bin; matching the summation order makes the sample indices bit-exact.
+__device__ __forceinline__ float aten_cpu_sum_w(const float* __restrict__ w, int nw, int lane) {
+  const int nv = nw >> 3, groups = nv >> 2;
+  const int k = lane >> 3, l = lane & 7;          // accumulator k, vector lane l
+  float acc = 0.f;
+  for (int i = 0; i < groups; ++i) acc = __fadd_rn(acc, __fadd_rn(__ldg(w + ((i * 4 + k) << 3) + l), 1e-5f));
+  if (k == 0)
+    for (int v = groups * 4; v < nv; ++v) acc = __fadd_rn(acc, __fadd_rn(__ldg(w + (v << 3) + l), 1e-5f));
+  const float a1 = __shfl_sync(FULL, acc, 8 + l), a2 = __shfl_sync(FULL, acc, 16 + l), a3 = __shfl_sync(FULL, acc, 24 + l);
+  acc = __fadd_rn(__fadd_rn(__fadd_rn(acc, a1), a2), a3);      // meaningful in lanes 0..7
+  float fin = 0.f;
+  for (int i = nv << 3; i < nw; ++i) fin = __fadd_rn(fin, __fadd_rn(__ldg(w + i), 1e-5f));
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-  const float total = (float)part;
+  for (int j = 0; j < 8; ++j) fin = __fadd_rn(fin, __shfl_sync(FULL, acc, j));
+  return fin;
+}
+
+__device__ __forceinline__ void build_cdf(const float* __restrict__ w, int nw, float* cdf, int lane) {
+  float total;
+  if (nw < 512) {
+    total = aten_cpu_sum_w(w, nw, lane);
+  } else {                                         // correctly rounded sum (double accumulation)
+    double part = 0.0;
+    for (int i = lane; i < nw; i += 32) part += (double)__fadd_rn(__ldg(w + i), 1e-5f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    total = (float)part;
+  }
   for (int i = lane; i < nw; i += 32) cdf[i + 1] = __fdiv_rn(__fadd_rn(__ldg(w + i), 1e-5f), total);
   __syncwarp();
-  if (lane == 0) {
+  if (lane == 0) {                                 // ATen's CPU cumsum: sequential, double accumulator, fp32 outputs
     double run = 0.0;
     cdf[0] = 0.f;
     for (int i = 1; i <= nw; ++i) { run += (double)cdf[i]; cdf[i] = (float)run; }
