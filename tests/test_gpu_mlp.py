@@ -126,7 +126,8 @@ def test_fp32_linear_primitives_ragged(cuda):
 
 
 def test_training_step_gradients_vs_reference_golden(cuda):
-    """BASELINE config 5 in miniature: render_rays forward + backward through both networks (fp32 path), loss =
+    """BASELINE config 5 in miniature: render_rays forward + backward through both networks (fp32 path), stratified
+    + inverse-CDF sampling with the reference's pytest-hook draws (configs/lego.txt trains with perturb = 1), loss =
     mse(fine) + mse(coarse) (run_nerf.py:776-791).  Parameter gradients within 1e-3 relative of the reference's."""
     import nerfail_b200 as nb
     g = golden("train_step.npz")
@@ -139,8 +140,8 @@ def test_training_step_gradients_vs_reference_golden(cuda):
     e4, _ = nb.get_embedder(4)
     query = nb.NetworkQuery(e10, e4, 1 << 16)
     rays, target = T(g["rays"]).to(cuda), T(g["target"]).to(cuda)
-    ret = nb.render_rays(rays, nets[0], query, 64, retraw=True, perturb=0., N_importance=128, network_fine=nets[1],
-                         white_bkgd=True, raw_noise_std=0.)
+    ret = nb.render_rays(rays, nets[0], query, 64, retraw=True, perturb=1., N_importance=128, network_fine=nets[1],
+                         white_bkgd=True, raw_noise_std=0., pytest=True)
     loss = nb.img2mse(ret["rgb_map"], target) + nb.img2mse(ret["rgb0"], target)
     loss.backward()
     assert abs(float(loss) - float(g["loss"])) < 1e-4 * float(g["loss"])

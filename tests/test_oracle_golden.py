@@ -99,7 +99,9 @@ def test_training_step_gradients():
     rays, target = T(g["rays"]), T(g["target"])
     sd_c = {k: v.clone().requires_grad_(True) for k, v in synth.make_non_degenerate(synth.random_state_dict(0), 0).items()}
     sd_f = {k: v.clone().requires_grad_(True) for k, v in synth.make_non_degenerate(synth.random_state_dict(1), 1).items()}
-    out = no.render_ray_batch(rays, sd_c, sd_f)
+    np.random.seed(0); t_rand = torch.Tensor(np.random.rand(rays.shape[0], 64))      # the reference's pytest hook
+    np.random.seed(0); u = torch.Tensor(np.random.rand(rays.shape[0], 128))
+    out = no.render_ray_batch(rays, sd_c, sd_f, t_rand=t_rand, u=u)
     loss = torch.mean((out["rgb_map"] - target) ** 2) + torch.mean((out["rgb0"] - target) ** 2)
     loss.backward()
     same(loss.detach().numpy(), g["loss"], tol=1e-6)
