@@ -145,6 +145,115 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
+    """Side measurements for the other BASELINE configs (reported under "extra", not part of `value`):
+    config 3 — NeRFail attack iteration: GaussNet gather forward + scatter backward over 100 views (800x800, P=3,
+               upstream gradient ~ N(0,1), classifier excluded), views sharded over ranks, ONE all-reduce
+               of grad_spatial_rgb per iteration (30.72 MB);
+    config 5 — NeRF retraining step: 4096 rays forward + backward through coarse + fine (fp32 layer kernels), rays
+               sharded over ranks, one all-reduce per network of the parameter gradients."""
+    from nerfail_b200 import dist as nd
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def sync_max(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    # ---- config 3: attack iteration (kernels + all-reduce) ----
+    P, Hh, Ww, V = 3, 800, 800, 100
+    mine = nd.shard_views(V, rank, world)
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    table = (torch.randn(P, Hh, Ww, 4, generator=g) * 5.0).to(dev).requires_grad_(True)
+    T = P * Hh * Ww
+    views = []
+    gd = torch.Generator(device=dev).manual_seed(100 + rank)
+    base_idx = torch.arange(Hh * Ww, device=dev).reshape(1, Hh, Ww, 1)
+    for v in mine[:16]:                      # 16 distinct views are enough to defeat caching; they are cycled below
+        idx = (base_idx + torch.randint(0, P, (1,), device=dev, generator=gd) * Hh * Ww
+               + torch.randint(-400, 401, (1, Hh, Ww, 8), device=dev, generator=gd)).clamp_(0, T - 1).float()
+        dist_ = torch.sort(torch.randn(1, Hh, Ww, 8, device=dev, generator=gd).abs() * 0.01, dim=-1).values
+        w_idx = ops.gauss_weights(torch.stack([dist_, idx], 1), 0.02)
+        ori = torch.randint(0, 256, (1, Hh, Ww, 4), device=dev, generator=gd, dtype=torch.uint8)
+        gx = torch.randn(1, Hh, Ww, 4, device=dev, generator=gd)
+        views.append((w_idx, ori, gx))
+    net = nb.gauss_net(dev, 0.02, None, "my_model", epsilon=32)
+    net.close_update_epsilon_3d()
+
+    def attack_iter():
+        grad = torch.zeros_like(table)
+        for i, _ in enumerate(mine):
+            w_idx, ori, gx = views[i % len(views)]
+            x, x_rgba = ops.gauss_gather_fwd(table.detach().reshape(-1, 4), w_idx, ori, 32.0)
+            ops.gauss_scatter_bwd(None, gx, x, w_idx, ori, 32.0, table.shape, out=grad)
+        nd.allreduce_sum_(grad)
+        return grad
+
+    for _ in range(2):
+        attack_iter()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = ev(), ev()
+    iters = 3
+    e0.record()
+    for _ in range(iters):
+        attack_iter()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = sync_max(e0.elapsed_time(e1)) / iters
+    px = V * Hh * Ww
+    out["attack_iteration"] = {"metric": "GaussNet fwd+bwd attack rays/s (1 pixel = 1 ray)", "value": px / (ms / 1e3), "unit": "rays/s",
+                               "ms_per_iteration": ms, "views": V, "views_per_rank": len(mine), "allreduce_bytes": int(table.numel() * 4),
+                               "algorithmic_bytes_per_pixel": 456, "achieved_GBps_per_gpu": len(mine) * Hh * Ww * 456 / (ms / 1e3) / 1e9,
+                               "scaling": "strong"}
+    del views, table
+
+    # ---- config 5: retraining step ----
+    N_rand = 4096
+    b, e = nd.shard_range(N_rand, rank, world)
+    K, _ = synth.intrinsics(H, W)
+    rays_all = ops.get_ray_batch(H, W, K, torch.tensor(synth.camera_ring(8)[1][:3, :4]), 2.0, 6.0, device=dev)
+    sel = torch.from_numpy(np.random.default_rng(0).choice(H * W, N_rand, replace=False)).to(dev)
+    rays_t = rays_all[sel][b:e].contiguous()
+    target = torch.rand(N_rand, 3, generator=torch.Generator().manual_seed(5))[b:e].to(dev)
+    kwt = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
+    kwt.update(perturb=1.0)
+    params_c, params_f = list(kw["network_fn"].parameters()), list(kw["network_fine"].parameters())
+
+    def train_step():
+        for p_ in params_c + params_f:
+            p_.grad = None
+        with torch.enable_grad():
+            ret = nb.render_rays(rays_t, retraw=True, **kwt)
+            loss = nb.img2mse(ret["rgb_map"], target) + nb.img2mse(ret["rgb0"], target)
+            loss.backward()
+        nd.allreduce_grads_(params_c, scale=1.0 / world)
+        nd.allreduce_grads_(params_f, scale=1.0 / world)
+        return loss
+
+    train_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(2):
+        train_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = sync_max(e0.elapsed_time(e1)) / 2
+    out["retraining_step"] = {"metric": "NeRF fwd+bwd rays/s (4096-ray batch, coarse+fine, fp32 layer kernels)", "value": N_rand / (ms / 1e3),
+                              "unit": "rays/s", "ms_per_step": ms, "rays_per_rank": int(e - b), "dtype": "f32", "optimizer_step": False,
+                              "allreduce_bytes": int(sum(p_.numel() for p_ in params_c + params_f) * 4), "scaling": "strong"}
+    for p_ in params_c + params_f:
+        p_.grad = None
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -152,6 +261,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the attack-iteration / retraining-step side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -252,6 +362,10 @@ def main():
         barrier()
         ms_e2e = max(e_start.elapsed_time(e_stop), 1e3 * (time.perf_counter() - t0))
 
+    extra = {}
+    if not args.no_extras:
+        extra = run_extras(args, dev, rank, world, dist, nb, ops, synth, kw)
+
     # MLP kernel time (both launches of every pass), measured inside the timed region on the launching stream
     mlp_ms = sum(e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3]) for e, _ in mlp_events)
     mlp_flop = sum(r * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE) * FLOP_PER_SAMPLE for _, r in mlp_events)
@@ -291,6 +405,8 @@ def main():
                          "avg_launch_ms": mlp_ms / max(1, n_mlp_launches),
                          "algorithmic_flop_per_sample": FLOP_PER_SAMPLE, "share_of_step": mlp_ms / ms},
         }
+        if extra:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             v, dt, cores = cpu_reference_rays_per_s(4096)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",

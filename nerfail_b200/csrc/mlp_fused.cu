@@ -35,7 +35,8 @@ constexpr int KCH = 64;            // K elements per smem chunk (= one 128-byte 
 constexpr int CHUNK_BYTES = TILE_M * KCH * 2;     // 16 KB: activation chunk and weight block alike
 constexpr int NSTEP = 10;          // MMA steps per tile: L0..L7, feature, views
 constexpr int NSTAGE = 4;          // weight ring depth
-constexpr int NUM_THREADS = 320;   // warp 0 producer, warp 1 MMA + TMEM owner, warps 2-5 slot 0, warps 6-9 slot 1
+constexpr int NUM_THREADS = 352;   // warp 0 producer, warp 1 MMA (slot 0) + TMEM owner, warps 2-5 / 6-9 epilogues of slot 0 / 1,
+                                   // warp 10 MMA issuer of slot 1 (cta_group::2 kernel)
 
 // weight blocks (16 KB each: 128 output rows x 64 K) per step, in consumption order (chunk-major, half-minor)
 __host__ __device__ constexpr int step_kchunks(int s) { return s == 0 ? 1 : (s == 5 || s == 9) ? 5 : 4; }
@@ -388,7 +389,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(W_FULL(s), (CG == 2 && leader) ? 2 : 1);      // CG=2 leader: own producer + the peer's relay
-      mbar_init(W_EMPTY(s), 1);
+      mbar_init(W_EMPTY(s), CG);                              // CG=2: released by the issuers of both tile slots
     }
     for (int g = 0; g < 2; ++g) { mbar_init(A_READY(g), 4 * CG); mbar_init(ACC_FULL(g), 1); }
     fence_barrier_init();
@@ -443,18 +444,18 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ================= MMA issuer (one thread) =================
-      uint32_t pos = 0;
-      uint32_t ready_phase[2] = {0, 0};
-      const uint64_t desc_hi = umma_desc(0) & 0xFFFFFFFF00000000ull;
-      auto desc_of = [&](uint32_t saddr) { return desc_hi | (uint64_t)(((saddr & 0x3FFFF) >> 4) | (1u << 16)); };
-      for (int64_t unit = group; unit < nunits; unit += ngroups) {
-        for (int s = 0; s < nsteps; ++s) {
-          const int kch = step_kchunks(s), halves = step_halves(s);
-          if constexpr (CG == 1) {
-            const uint32_t idesc = umma_idesc_mn(128, 128);
+  } else if (warp == 1 || warp == 10) {
+    const uint64_t desc_hi = umma_desc(0) & 0xFFFFFFFF00000000ull;
+    auto desc_of = [&](uint32_t saddr) { return desc_hi | (uint64_t)(((saddr & 0x3FFFF) >> 4) | (1u << 16)); };
+    if constexpr (CG == 1) {
+      if (warp == 1 && lane == 0) {
+        // ================= MMA issuer (one thread, both slots in turn) =================
+        uint32_t pos = 0;
+        uint32_t ready_phase[2] = {0, 0};
+        const uint32_t idesc = umma_idesc_mn(128, 128);
+        for (int64_t unit = group; unit < nunits; unit += ngroups) {
+          for (int s = 0; s < nsteps; ++s) {
+            const int kch = step_kchunks(s), halves = step_halves(s);
             for (int g = 0; g < 2; ++g) {
               mbar_wait(A_READY(g), ready_phase[g], abort_flag);
               ready_phase[g] ^= 1;
@@ -476,59 +477,51 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
               }
               umma_commit_group<1>(ACC_FULL(g));
             }
-          } else {
-            const uint32_t idesc = umma_idesc_mn(256, halves == 2 ? 256 : 128);
-            const int main_ch = kch < NSTAGE ? kch : NSTAGE;     // chunks resident together; a 5th one goes last
-            const uint32_t p0 = pos;
-            for (int g = 0; g < 2; ++g) {
-              mbar_wait(A_READY(g), ready_phase[g], abort_flag);
-              ready_phase[g] ^= 1;
-              tc_fence_after();
-              const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
-              const uint32_t d = tmem_base + g * 256;
-              for (int c = 0; c < main_ch; ++c) {
-                const uint32_t p = p0 + c;
-                const int stage = p & (NSTAGE - 1);
-                if (g == 0) { mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag); tc_fence_after(); }
-                const uint64_t ad = desc_of(a_chunk_addr(s, c, act, pe));
-                const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
-#pragma unroll
-                for (int k = 0; k < KCH / 16; ++k)
-                  umma_issue<2>(d, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
-                if (g == 1) umma_commit_group<2>(W_EMPTY(stage));   // both slots have consumed the block
-              }
-              if (kch == main_ch) umma_commit_group<2>(ACC_FULL(g));
-            }
-            if (kch > main_ch) {                                  // the encoding chunk of steps 5 and 9
-              const uint32_t p = p0 + main_ch;
-              const int stage = p & (NSTAGE - 1);
-              mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag);
-              tc_fence_after();
-              const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
-              for (int g = 0; g < 2; ++g) {
-                const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
-                const uint64_t ad = desc_of(a_chunk_addr(s, main_ch, act, pe));
-#pragma unroll
-                for (int k = 0; k < KCH / 16; ++k)
-                  umma_issue<2>(tmem_base + g * 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
-                if (g == 1) umma_commit_group<2>(W_EMPTY(stage));
-                umma_commit_group<2>(ACC_FULL(g));
-              }
-            }
-            pos += kch;
           }
         }
       }
-    } else if (CG == 2 && lane == 0 && !leader) {
-      // ================= peer relay: tells the leader when this CTA's half of a block has landed =================
-      uint32_t pos = 0;
-      for (int64_t unit = group; unit < nunits; unit += ngroups)
-        for (int s = 0; s < nsteps; ++s)
-          for (int c = 0; c < step_kchunks(s); ++c, ++pos) {
-            const int stage = pos & (NSTAGE - 1);
-            mbar_wait(W_FULL(stage), (pos >> 2) & 1, abort_flag);
-            mbar_arrive_remote(W_FULL(stage), 0);
+    } else {
+      if (lane == 0 && leader) {
+        // ================= MMA issuers: warp 1 drives tile slot 0, warp 10 drives tile slot 1 =================
+        // Both walk the same sequence of weight blocks through the shared ring; a block is released (W_EMPTY, count 2)
+        // once both have consumed it, so neither can run more than NSTAGE blocks ahead of the other and the tensor
+        // pipe serves whichever slot has its A operand ready.
+        const int g = (warp == 1) ? 0 : 1;
+        const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
+        const uint32_t d = tmem_base + g * 256;
+        uint32_t pos = 0, ready_phase = 0;
+        for (int64_t unit = group; unit < nunits; unit += ngroups) {
+          for (int s = 0; s < nsteps; ++s) {
+            const int kch = step_kchunks(s);
+            const uint32_t idesc = umma_idesc_mn(256, step_halves(s) == 2 ? 256 : 128);
+            mbar_wait(A_READY(g), ready_phase, abort_flag);
+            ready_phase ^= 1;
+            tc_fence_after();
+            for (int c = 0; c < kch; ++c, ++pos) {
+              const int stage = pos & (NSTAGE - 1);
+              mbar_wait(W_FULL(stage), (pos >> 2) & 1, abort_flag);
+              tc_fence_after();
+              const uint64_t ad = desc_of(a_chunk_addr(s, c, act, pe));
+              const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
+#pragma unroll
+              for (int k = 0; k < KCH / 16; ++k)
+                umma_issue<2>(d, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+              umma_commit_group<2>(W_EMPTY(stage));
+            }
+            umma_commit_group<2>(ACC_FULL(g));
           }
+        }
+      } else if (warp == 1 && lane == 0) {
+        // ================= peer relay: tells the leader when this CTA's half of a block has landed =================
+        uint32_t pos = 0;
+        for (int64_t unit = group; unit < nunits; unit += ngroups)
+          for (int s = 0; s < nsteps; ++s)
+            for (int c = 0; c < step_kchunks(s); ++c, ++pos) {
+              const int stage = pos & (NSTAGE - 1);
+              mbar_wait(W_FULL(stage), (pos >> 2) & 1, abort_flag);
+              mbar_arrive_remote(W_FULL(stage), 0);
+            }
+      }
     }
   } else {
     // ================= input stage + epilogues (one thread = one sample = one TMEM lane) =================

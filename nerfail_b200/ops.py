@@ -395,11 +395,13 @@ def gauss_gather_fwd(table, w_idx, ori_u8, eps, minmax=None):
     return x, x_rgba
 
 
-def gauss_scatter_bwd(g_x, g_xrgba, x, w_idx, ori_u8, eps, table_shape):
+def gauss_scatter_bwd(g_x, g_xrgba, x, w_idx, ori_u8, eps, table_shape, out=None):
+    """grad w.r.t. the [P,H,W,4] table; accumulates into `out` when given (e.g. across the views of an iteration)."""
     T = int(np.prod(table_shape)) // 4
     B = w_idx.shape[0]
     HW = w_idx.shape[2] * w_idx.shape[3]
-    g_table = torch.zeros(table_shape, dtype=torch.float32, device=w_idx.device)
+    g_table = out if out is not None else torch.zeros(table_shape, dtype=torch.float32, device=w_idx.device)
+    assert g_table.is_contiguous() and g_table.numel() == T * 4
     g_x = None if g_x is None else _f32(g_x)
     g_xrgba = None if g_xrgba is None else _f32(g_xrgba)
     with torch.cuda.device(w_idx.device):
