@@ -35,8 +35,7 @@ constexpr int KCH = 64;            // K elements per smem chunk (= one 128-byte 
 constexpr int CHUNK_BYTES = TILE_M * KCH * 2;     // 16 KB: activation chunk and weight block alike
 constexpr int NSTEP = 10;          // MMA steps per tile: L0..L7, feature, views
 constexpr int NSTAGE = 4;          // weight ring depth
-constexpr int NUM_THREADS = 352;   // warp 0 producer, warp 1 MMA (slot 0) + TMEM owner, warps 2-5 / 6-9 epilogues of slot 0 / 1,
-                                   // warp 10 MMA issuer of slot 1 (cta_group::2 kernel)
+constexpr int NUM_THREADS = 320;   // warp 0 producer, warp 1 MMA + TMEM owner, warps 2-5 slot 0, warps 6-9 slot 1
 
 // weight blocks (16 KB each: 128 output rows x 64 K) per step, in consumption order (chunk-major, half-minor)
 __host__ __device__ constexpr int step_kchunks(int s) { return s == 0 ? 1 : (s == 5 || s == 9) ? 5 : 4; }
@@ -190,11 +189,43 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must not hang the GPU.  On timeout the abort flag is raised, every later wait
 // in the grid falls through, the kernel finishes with garbage and the host reports NFB_E_CUDA.
+// The spin loop lives inside ONE asm statement so that the compiler sees straight-line code: control flow around
+// the waits stays warp-uniform and the MMA warp can keep descriptors in uniform registers (no per-instruction
+// ELECT + R2UR when issuing tcgen05.mma).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22) || ((spins & 1023u) == 0 && *abort_flag)) { *abort_flag = 1; break; }
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .u32 n, f;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra NFB_DONE;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "NFB_SPIN:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra NFB_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "and.b32 f, n, 1023;\n\t"
+      "setp.ne.u32 q, f, 0;\n\t"
+      "@q bra NFB_SPIN;\n\t"
+      "ld.volatile.global.u32 f, [%2];\n\t"
+      "setp.ne.u32 q, f, 0;\n\t"
+      "@q bra NFB_DONE;\n\t"
+      "setp.lt.u32 q, n, 4194304;\n\t"
+      "@q bra NFB_SPIN;\n\t"
+      "mov.u32 f, 1;\n\t"
+      "st.volatile.global.u32 [%2], f;\n\t"
+      "NFB_DONE:\n\t"
+      "}"
+      :: "r"(bar), "r"(parity), "l"(abort_flag) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -389,7 +420,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(W_FULL(s), (CG == 2 && leader) ? 2 : 1);      // CG=2 leader: own producer + the peer's relay
-      mbar_init(W_EMPTY(s), CG);                              // CG=2: released by the issuers of both tile slots
+      mbar_init(W_EMPTY(s), 1);
     }
     for (int g = 0; g < 2; ++g) { mbar_init(A_READY(g), 4 * CG); mbar_init(ACC_FULL(g), 1); }
     fence_barrier_init();
@@ -414,29 +445,31 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
   const int64_t group = blockIdx.x / CG, ngroups = gridDim.x / CG;
 
   if (warp == 0) {
-    // ================= weight producer (one thread) =================
-    if (lane == 0) {
-      uint32_t pos = 0;
-      for (int64_t unit = group; unit < nunits; unit += ngroups) {
-        for (int s = 0; s < nsteps; ++s) {
-          const int kch = step_kchunks(s), halves = step_halves(s);
-          const char* src = reinterpret_cast<const char*>(a.image) + (int64_t)step_block0(s) * CHUNK_BYTES;
-          if constexpr (CG == 1) {
-            for (int g = 0; g < 2; ++g)
-              for (int b = 0; b < kch * halves; ++b, ++pos) {
-                const int stage = pos & (NSTAGE - 1);
-                mbar_wait(W_EMPTY(stage), ((pos >> 2) & 1) ^ 1, abort_flag);
+    // ================= weight producer (whole warp waits, one elected lane issues the bulk copies) =================
+    uint32_t pos = 0;
+    for (int64_t unit = group; unit < nunits; unit += ngroups) {
+      for (int s = 0; s < nsteps; ++s) {
+        const int kch = step_kchunks(s), halves = step_halves(s);
+        const char* src = reinterpret_cast<const char*>(a.image) + (int64_t)step_block0(s) * CHUNK_BYTES;
+        if constexpr (CG == 1) {
+          for (int g = 0; g < 2; ++g)
+            for (int b = 0; b < kch * halves; ++b, ++pos) {
+              const int stage = pos & (NSTAGE - 1);
+              mbar_wait(W_EMPTY(stage), ((pos >> 2) & 1) ^ 1, abort_flag);
+              if (elect_one()) {
                 mbar_arrive_expect_tx(W_FULL(stage), CHUNK_BYTES);
                 bulk_g2s(base + SM_W + stage * CHUNK_BYTES, src + (int64_t)b * CHUNK_BYTES, CHUNK_BYTES, W_FULL(stage));
               }
-          } else {
-            // this CTA's half of every block, once per step (both slots reuse it): N rows [rank*N/2, (rank+1)*N/2)
-            const uint32_t bytes = (halves == 2) ? CHUNK_BYTES : CHUNK_BYTES / 2;
-            for (int c = 0; c < kch; ++c, ++pos) {
-              const int stage = pos & (NSTAGE - 1);
-              const char* blk = (halves == 2) ? src + (int64_t)(c * 2 + rank) * CHUNK_BYTES
-                                              : src + (int64_t)c * CHUNK_BYTES + rank * (CHUNK_BYTES / 2);
-              mbar_wait(W_EMPTY(stage), ((pos >> 2) & 1) ^ 1, abort_flag);
+            }
+        } else {
+          // this CTA's half of every block, once per step (both slots reuse it): N rows [rank*N/2, (rank+1)*N/2)
+          const uint32_t bytes = (halves == 2) ? CHUNK_BYTES : CHUNK_BYTES / 2;
+          for (int c = 0; c < kch; ++c, ++pos) {
+            const int stage = pos & (NSTAGE - 1);
+            const char* blk = (halves == 2) ? src + (int64_t)(c * 2 + rank) * CHUNK_BYTES
+                                            : src + (int64_t)c * CHUNK_BYTES + rank * (CHUNK_BYTES / 2);
+            mbar_wait(W_EMPTY(stage), ((pos >> 2) & 1) ^ 1, abort_flag);
+            if (elect_one()) {
               mbar_arrive_expect_tx(W_FULL(stage), bytes);
               bulk_g2s(base + SM_W + stage * CHUNK_BYTES, blk, bytes, W_FULL(stage));
             }
@@ -444,21 +477,24 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
         }
       }
     }
-  } else if (warp == 1 || warp == 10) {
-    const uint64_t desc_hi = umma_desc(0) & 0xFFFFFFFF00000000ull;
-    auto desc_of = [&](uint32_t saddr) { return desc_hi | (uint64_t)(((saddr & 0x3FFFF) >> 4) | (1u << 16)); };
-    if constexpr (CG == 1) {
-      if (warp == 1 && lane == 0) {
-        // ================= MMA issuer (one thread, both slots in turn) =================
-        uint32_t pos = 0;
-        uint32_t ready_phase[2] = {0, 0};
-        const uint32_t idesc = umma_idesc_mn(128, 128);
-        for (int64_t unit = group; unit < nunits; unit += ngroups) {
-          for (int s = 0; s < nsteps; ++s) {
-            const int kch = step_kchunks(s), halves = step_halves(s);
+  } else if (warp == 1) {
+    // Warp-uniform control flow: every lane walks the loops and waits on the barriers; one elected lane issues the
+    // tcgen05.mma / tcgen05.commit instructions, whose descriptors then live in uniform registers.
+    const uint32_t dlo_or = 1u << 16;
+    const uint32_t dhi = (uint32_t)(umma_desc(0) >> 32);
+    auto desc_of = [&](uint32_t saddr) { return ((uint64_t)dhi << 32) | (uint64_t)(((saddr & 0x3FFFF) >> 4) | dlo_or); };
+    if (leader) {
+      // ================= MMA issuer =================
+      uint32_t pos = 0, ready_phase0 = 0, ready_phase1 = 0;
+      for (int64_t unit = group; unit < nunits; unit += ngroups) {
+        for (int s = 0; s < nsteps; ++s) {
+          const int kch = step_kchunks(s), halves = step_halves(s);
+          if constexpr (CG == 1) {
+            const uint32_t idesc = umma_idesc_mn(128, 128);
+#pragma unroll
             for (int g = 0; g < 2; ++g) {
-              mbar_wait(A_READY(g), ready_phase[g], abort_flag);
-              ready_phase[g] ^= 1;
+              mbar_wait(A_READY(g), g == 0 ? ready_phase0 : ready_phase1, abort_flag);
+              if (g == 0) ready_phase0 ^= 1; else ready_phase1 ^= 1;
               tc_fence_after();
               const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
               for (int c = 0; c < kch; ++c) {
@@ -469,59 +505,75 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
                   tc_fence_after();
                   const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
                   const uint32_t d = tmem_base + g * 256 + h * 128;
+                  if (elect_one()) {
 #pragma unroll
-                  for (int k = 0; k < KCH / 16; ++k)
-                    umma_issue<1>(d, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
-                  umma_commit_group<1>(W_EMPTY(stage));
+                    for (int k = 0; k < KCH / 16; ++k)
+                      umma_issue<1>(d, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    umma_commit_group<1>(W_EMPTY(stage));
+                    if (c == kch - 1 && h == halves - 1) umma_commit_group<1>(ACC_FULL(g));
+                  }
                 }
               }
-              umma_commit_group<1>(ACC_FULL(g));
             }
-          }
-        }
-      }
-    } else {
-      if (lane == 0 && leader) {
-        // ================= MMA issuers: warp 1 drives tile slot 0, warp 10 drives tile slot 1 =================
-        // Both walk the same sequence of weight blocks through the shared ring; a block is released (W_EMPTY, count 2)
-        // once both have consumed it, so neither can run more than NSTAGE blocks ahead of the other and the tensor
-        // pipe serves whichever slot has its A operand ready.
-        const int g = (warp == 1) ? 0 : 1;
-        const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
-        const uint32_t d = tmem_base + g * 256;
-        uint32_t pos = 0, ready_phase = 0;
-        for (int64_t unit = group; unit < nunits; unit += ngroups) {
-          for (int s = 0; s < nsteps; ++s) {
-            const int kch = step_kchunks(s);
-            const uint32_t idesc = umma_idesc_mn(256, step_halves(s) == 2 ? 256 : 128);
-            mbar_wait(A_READY(g), ready_phase, abort_flag);
-            ready_phase ^= 1;
-            tc_fence_after();
-            for (int c = 0; c < kch; ++c, ++pos) {
-              const int stage = pos & (NSTAGE - 1);
-              mbar_wait(W_FULL(stage), (pos >> 2) & 1, abort_flag);
+          } else {
+            const uint32_t idesc = umma_idesc_mn(256, halves == 2 ? 256 : 128);
+            const int main_ch = kch < NSTAGE ? kch : NSTAGE;     // chunks resident together; a 5th one goes last
+            const uint32_t p0 = pos;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(A_READY(g), g == 0 ? ready_phase0 : ready_phase1, abort_flag);
+              if (g == 0) ready_phase0 ^= 1; else ready_phase1 ^= 1;
               tc_fence_after();
-              const uint64_t ad = desc_of(a_chunk_addr(s, c, act, pe));
+              const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
+              const uint32_t d = tmem_base + g * 256;
+              for (int c = 0; c < main_ch; ++c) {
+                const uint32_t p = p0 + c;
+                const int stage = p & (NSTAGE - 1);
+                if (g == 0) { mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag); tc_fence_after(); }
+                const uint64_t ad = desc_of(a_chunk_addr(s, c, act, pe));
+                const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < KCH / 16; ++k)
+                    umma_issue<2>(d, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                  if (g == 1) umma_commit_group<2>(W_EMPTY(stage));   // both slots have consumed the block
+                  if (kch == main_ch && c == main_ch - 1) umma_commit_group<2>(ACC_FULL(g));
+                }
+              }
+            }
+            if (kch > main_ch) {                                  // the encoding chunk of steps 5 and 9
+              const uint32_t p = p0 + main_ch;
+              const int stage = p & (NSTAGE - 1);
+              mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag);
+              tc_fence_after();
               const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
 #pragma unroll
-              for (int k = 0; k < KCH / 16; ++k)
-                umma_issue<2>(d, ad + 2 * k, bd + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
-              umma_commit_group<2>(W_EMPTY(stage));
+              for (int g = 0; g < 2; ++g) {
+                const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
+                const uint64_t ad = desc_of(a_chunk_addr(s, main_ch, act, pe));
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < KCH / 16; ++k)
+                    umma_issue<2>(tmem_base + g * 256, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                  if (g == 1) umma_commit_group<2>(W_EMPTY(stage));
+                  umma_commit_group<2>(ACC_FULL(g));
+                }
+              }
             }
-            umma_commit_group<2>(ACC_FULL(g));
+            pos += kch;
           }
         }
-      } else if (warp == 1 && lane == 0) {
-        // ================= peer relay: tells the leader when this CTA's half of a block has landed =================
-        uint32_t pos = 0;
-        for (int64_t unit = group; unit < nunits; unit += ngroups)
-          for (int s = 0; s < nsteps; ++s)
-            for (int c = 0; c < step_kchunks(s); ++c, ++pos) {
-              const int stage = pos & (NSTAGE - 1);
-              mbar_wait(W_FULL(stage), (pos >> 2) & 1, abort_flag);
-              mbar_arrive_remote(W_FULL(stage), 0);
-            }
       }
+    } else if (CG == 2) {
+      // ================= peer relay: tells the leader when this CTA's half of a block has landed =================
+      uint32_t pos = 0;
+      for (int64_t unit = group; unit < nunits; unit += ngroups)
+        for (int s = 0; s < nsteps; ++s)
+          for (int c = 0; c < step_kchunks(s); ++c, ++pos) {
+            const int stage = pos & (NSTAGE - 1);
+            mbar_wait(W_FULL(stage), (pos >> 2) & 1, abort_flag);
+            if (elect_one()) mbar_arrive_remote(W_FULL(stage), 0);
+          }
     }
   } else {
     // ================= input stage + epilogues (one thread = one sample = one TMEM lane) =================
