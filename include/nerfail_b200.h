@@ -96,6 +96,12 @@ NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, co
                       const float* rays, const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg,
                       void* stream);
 
+/* Profiling aid: the full forward (mode 1) while CTA 0 records a timeline of its barrier waits into
+ * trace [3 roles][2048 events][4] uint64 = (tag, clock begin, clock end, aux); roles: 0 weight producer, 1 MMA warp,
+ * 2 epilogue warps.  scripts/trace_mlp.py decodes it.                                                     */
+NFB_API int nfb_mlp_fwd_trace(const nfb_mlp_t* h, const float* rays, const float* z_vals, int R, int S, float* raw,
+                              unsigned long long* trace, void* stream);
+
 /* Positional encoding to HBM (layer-wise fp32 path only).
  * replaces: run_nerf_helpers.py:36-50.  x [M,3] -> out [M, 3+6*L] at column offset col0 of a row pitch ld. */
 NFB_API int nfb_embed(const float* x, int64_t M, int L, float* out, int ld, int col0, int64_t row_repeat, void* stream);

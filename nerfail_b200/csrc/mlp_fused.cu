@@ -336,7 +336,9 @@ struct FwdArgs {
   float* raw;               // [M,4]
   int nsteps;               // 10 normally; < 10 = debug: stop after that many MMA steps and dump activations
   float* dbg;               // [M,256] fp32 post-activation values of the last executed step (debug only)
+  unsigned long long* trace;   // optional timeline of CTA 0: [3 roles][TRACE_CAP][4] = tag, t_begin, t_end, aux (profiling aid)
 };
+constexpr int TRACE_CAP = 2048;
 
 // ---- cluster / cta_group::2 helpers ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -416,6 +418,15 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
   const bool leader = rank == 0;
   volatile int* abort_flag = a.abort_flag;
   const int nsteps = a.nsteps;
+  const bool tracing = a.trace != nullptr && blockIdx.x == 0;
+  int trace_n = 0;
+  auto trace_evt = [&](int role, unsigned long long tag, unsigned long long t0, unsigned long long t1, unsigned long long aux) {
+    if (tracing && lane == 0 && trace_n < TRACE_CAP) {
+      unsigned long long* e = a.trace + ((size_t)role * TRACE_CAP + trace_n) * 4;
+      e[0] = tag; e[1] = t0; e[2] = t1; e[3] = aux;
+      ++trace_n;
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -468,11 +479,13 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             const int stage = pos & (NSTAGE - 1);
             const char* blk = (halves == 2) ? src + (int64_t)(c * 2 + rank) * CHUNK_BYTES
                                             : src + (int64_t)c * CHUNK_BYTES + rank * (CHUNK_BYTES / 2);
+            const unsigned long long t0 = tracing ? clock64() : 0;
             mbar_wait(W_EMPTY(stage), ((pos >> 2) & 1) ^ 1, abort_flag);
             if (elect_one()) {
               mbar_arrive_expect_tx(W_FULL(stage), bytes);
               bulk_g2s(base + SM_W + stage * CHUNK_BYTES, blk, bytes, W_FULL(stage));
             }
+            if (tracing) trace_evt(0, pos, t0, clock64(), (unsigned long long)s << 8 | c);
           }
         }
       }
@@ -521,7 +534,9 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             const uint32_t p0 = pos;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
+              const unsigned long long ta = tracing ? clock64() : 0;
               mbar_wait(A_READY(g), g == 0 ? ready_phase0 : ready_phase1, abort_flag);
+              if (tracing) trace_evt(1, 0x1000 | (s << 4) | g, ta, clock64(), 0);
               if (g == 0) ready_phase0 ^= 1; else ready_phase1 ^= 1;
               tc_fence_after();
               const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
@@ -529,7 +544,12 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
               for (int c = 0; c < main_ch; ++c) {
                 const uint32_t p = p0 + c;
                 const int stage = p & (NSTAGE - 1);
-                if (g == 0) { mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag); tc_fence_after(); }
+                if (g == 0) {
+                  const unsigned long long tw = tracing ? clock64() : 0;
+                  mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag);
+                  tc_fence_after();
+                  if (tracing) trace_evt(1, 0x2000 | (s << 4) | c, tw, clock64(), p);
+                }
                 const uint64_t ad = desc_of(a_chunk_addr(s, c, act, pe));
                 const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
                 if (elect_one()) {
@@ -620,7 +640,9 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
 
       float sigma = 0.f;
       for (int s = 0; s < nsteps; ++s) {
+        const unsigned long long te = tracing ? clock64() : 0;
         mbar_wait(ACC_FULL(g), full_phase, abort_flag);
+        if (tracing && (warp & 3) == 2) trace_evt(2, 0x3000 | (s << 4) | g, te, clock64(), 0);
         full_phase ^= 1;
         tc_fence_after();
         const bool last = (s == nsteps - 1);
@@ -689,6 +711,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             store_row_chunk(pe, row, f);
           }
           if (!last) signal_a_ready();
+          if (tracing && (warp & 3) == 2) trace_evt(2, 0x4000 | (s << 4) | g, clock64(), clock64(), 0);
         } else {
           // ---- views layer epilogue: relu(acc + b) . w_rgb -> raw ----
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
@@ -800,7 +823,8 @@ int nfb_mlp_status(nfb_mlp_t* h) {
 }
 
 static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs, const float* rays,
-                      const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg, void* stream) {
+                      const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg, void* stream,
+                      unsigned long long* trace = nullptr) {
   NFB_REQUIRE(h && raw, "mlp_fwd: null handle or output");
   NFB_REQUIRE(R >= 0 && S > 0, "mlp_fwd: R=%d S=%d", R, S);
   NFB_REQUIRE(mode == 0 ? (pts && dirs) : (mode == 1 && rays && z_vals), "mlp_fwd: inputs missing for mode %d", mode);
@@ -810,7 +834,7 @@ static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const floa
   nfb::FwdArgs a;
   a.image = h->image; a.side = h->side; a.abort_flag = h->abort_flag;
   a.mode = mode; a.pts = pts; a.dirs = dirs; a.rays = rays; a.z_vals = z_vals;
-  a.M = (int64_t)R * S; a.S = S; a.raw = raw; a.nsteps = nsteps; a.dbg = dbg;
+  a.M = (int64_t)R * S; a.S = S; a.raw = raw; a.nsteps = nsteps; a.dbg = dbg; a.trace = trace;
   // NERFAIL_B200_CG=1 selects the single-CTA variant (cta_group::1); default is the CTA-pair kernel (cta_group::2).
   static const int cg = []() { const char* e = getenv("NERFAIL_B200_CG"); return (e && e[0] == '1') ? 1 : 2; }();
   const int64_t rows_per_unit = 2 * nfb::TILE_M * cg;
@@ -846,6 +870,12 @@ int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const floa
                       const float* rays, const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg,
                       void* stream) {
   return mlp_launch(h, mode, pts, dirs, rays, z_vals, R, S, raw, nsteps, dbg, stream);
+}
+
+// Profiling aid: full forward with a timeline of CTA 0 written to trace [3][2048][4] uint64 (see FwdArgs::trace).
+int nfb_mlp_fwd_trace(const nfb_mlp_t* h, const float* rays, const float* z_vals, int R, int S, float* raw,
+                      unsigned long long* trace, void* stream) {
+  return mlp_launch(h, 1, nullptr, nullptr, rays, z_vals, R, S, raw, nfb::NSTEP, nullptr, stream, trace);
 }
 
 }  // extern "C"
