@@ -35,7 +35,7 @@ constexpr int KCH = 64;            // K elements per smem chunk (= one 128-byte 
 constexpr int CHUNK_BYTES = TILE_M * KCH * 2;     // 16 KB: activation chunk and weight block alike
 constexpr int NSTEP = 10;          // MMA steps per tile: L0..L7, feature, views
 constexpr int NSTAGE = 4;          // weight ring depth
-constexpr int NUM_THREADS = 320;   // warp 0 producer, warp 1 MMA + TMEM owner, warps 2-5 slot 0, warps 6-9 slot 1
+constexpr int NUM_THREADS = 576;   // warp 0 producer, warp 1 MMA + TMEM owner, warps 2-9 slot 0, warps 10-17 slot 1
 
 // weight blocks (16 KB each: 128 output rows x 64 K) per step, in consumption order (chunk-major, half-minor)
 __host__ __device__ constexpr int step_kchunks(int s) { return s == 0 ? 1 : (s == 5 || s == 9) ? 5 : 4; }
@@ -433,7 +433,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
       mbar_init(W_FULL(s), (CG == 2 && leader) ? 2 : 1);      // CG=2 leader: own producer + the peer's relay
       mbar_init(W_EMPTY(s), 1);
     }
-    for (int g = 0; g < 2; ++g) { mbar_init(A_READY(g), 4 * CG); mbar_init(ACC_FULL(g), 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(A_READY(g), 8 * CG); mbar_init(ACC_FULL(g), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {   // TMEM: all 512 columns (two 128x256 fp32 accumulators per CTA)
@@ -596,15 +596,23 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
           }
     }
   } else {
-    // ================= input stage + epilogues (one thread = one sample = one TMEM lane) =================
-    const int g = (warp - 2) >> 2;                    // slot
-    const int row = ((warp & 3) << 5) + lane;         // TMEM lane quarter is fixed by warp id % 4
+    // ================= input stage + epilogues =================
+    // 8 warps per tile slot: warp id % 4 fixes the TMEM lane quarter (32 samples), (warp - 2) / 4 % 2 picks the column
+    // half, so one sample's accumulator row is drained by two threads (128 columns each).  tcgen05.ld retires one
+    // 32-column load per ~94 cycles per warp (measured, scripts/ubench/tmem_ld.cu); two warps per quarter halve the
+    // drain latency that the other slot's MMAs have to cover.
+    const int e = warp - 2;
+    const int g = e >> 3;                             // slot
+    const int hcol = (e >> 2) & 1;                    // column half of this thread
+    const int q = warp & 3;                           // TMEM lane quarter
+    const int row = (q << 5) + lane;
     const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES;
     const uint32_t pe = base + SM_PE + g * CHUNK_BYTES;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) << 5) << 16) + g * 256;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q << 5) << 16) + g * 256;
+    const uint32_t pair_bar = 1 + g * 4 + q;          // named barrier shared by the two warps of a (slot, quarter)
     const MlpSide* __restrict__ sd = a.side;
     uint32_t full_phase = 0;
-    auto signal_a_ready = [&]() {                     // this warp's rows of the A operand are in shared memory
+    auto signal_a_ready = [&]() {                     // this warp's part of the A operand is in shared memory
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
@@ -612,26 +620,32 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
         if (CG == 1 || leader) mbar_arrive(A_READY(g)); else mbar_arrive_remote(A_READY(g), 0);
       }
     };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" :: "r"(pair_bar) : "memory"); };
+    // shared-memory scratch (generic proxy) used to combine the two column halves of a row
+    float* scratch_pe = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + SM_PE + g * CHUNK_BYTES);
+    float* scratch_act = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + SM_ACT + g * 4 * CHUNK_BYTES);
+
     for (int64_t unit = group; unit < nunits; unit += ngroups) {
       const int64_t m = unit * ROWS_PER_UNIT + (int64_t)g * (TILE_M * CG) + rank * TILE_M + row;
       const bool live = m < a.M;
-      // ---- input stage ----
-      float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
-      if (live) {
-        const int64_t r = m / a.S;
-        if (a.mode == 0) {
-          px = __ldg(a.pts + m * 3); py = __ldg(a.pts + m * 3 + 1); pz = __ldg(a.pts + m * 3 + 2);
-          vx = __ldg(a.dirs + r * 3); vy = __ldg(a.dirs + r * 3 + 1); vz = __ldg(a.dirs + r * 3 + 2);
-        } else {
-          const float* ray = a.rays + r * 11;
-          const float z = __ldg(a.z_vals + m);
-          px = __fadd_rn(__ldg(ray), __fmul_rn(__ldg(ray + 3), z));        // run_nerf.py:381
-          py = __fadd_rn(__ldg(ray + 1), __fmul_rn(__ldg(ray + 4), z));
-          pz = __fadd_rn(__ldg(ray + 2), __fmul_rn(__ldg(ray + 5), z));
-          vx = __ldg(ray + 8); vy = __ldg(ray + 9); vz = __ldg(ray + 10);
+      // ---- input stage (the column-half-0 thread of each row encodes the point) ----
+      float vx = 0.f, vy = 0.f, vz = 0.f;
+      if (hcol == 0) {
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (live) {
+          const int64_t r = m / a.S;
+          if (a.mode == 0) {
+            px = __ldg(a.pts + m * 3); py = __ldg(a.pts + m * 3 + 1); pz = __ldg(a.pts + m * 3 + 2);
+            vx = __ldg(a.dirs + r * 3); vy = __ldg(a.dirs + r * 3 + 1); vz = __ldg(a.dirs + r * 3 + 2);
+          } else {
+            const float* ray = a.rays + r * 11;
+            const float z = __ldg(a.z_vals + m);
+            px = __fadd_rn(__ldg(ray), __fmul_rn(__ldg(ray + 3), z));        // run_nerf.py:381
+            py = __fadd_rn(__ldg(ray + 1), __fmul_rn(__ldg(ray + 4), z));
+            pz = __fadd_rn(__ldg(ray + 2), __fmul_rn(__ldg(ray + 5), z));
+            vx = __ldg(ray + 8); vy = __ldg(ray + 9); vz = __ldg(ray + 10);
+          }
         }
-      }
-      {
         float f[64];
         encode3<L_PTS>(px, py, pz, f);
         store_row_chunk(pe, row, f);
@@ -642,7 +656,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
       for (int s = 0; s < nsteps; ++s) {
         const unsigned long long te = tracing ? clock64() : 0;
         mbar_wait(ACC_FULL(g), full_phase, abort_flag);
-        if (tracing && (warp & 3) == 2) trace_evt(2, 0x3000 | (s << 4) | g, te, clock64(), 0);
+        if (tracing && e == 0) trace_evt(2, 0x3000 | (s << 4) | g, te, clock64(), 0);
         full_phase ^= 1;
         tc_fence_after();
         const bool last = (s == nsteps - 1);
@@ -651,50 +665,47 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
           const bool relu = (s < 8);
           float sig_acc = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {                // 64 accumulator columns = one activation K-chunk
-            uint32_t v0[32], v1[32];
-            tmem_ld32(tmem_row + c * 64, v0);
-            tmem_ld32(tmem_row + c * 64 + 32, v1);
-            float4 b4[16];
+          for (int cc = 0; cc < 4; ++cc) {             // 4 x 32 accumulator columns of this thread's half
+            const int col0 = hcol * 128 + cc * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem_row + col0, v);
+            float4 b4[8];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) b4[q] = __ldg(reinterpret_cast<const float4*>(bias + c * 64) + q);
+            for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
             tmem_ld_wait();
-            float h[64];
+            float h[32];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              h[4 * q] = __uint_as_float(v0[4 * q]) + b4[q].x;
-              h[4 * q + 1] = __uint_as_float(v0[4 * q + 1]) + b4[q].y;
-              h[4 * q + 2] = __uint_as_float(v0[4 * q + 2]) + b4[q].z;
-              h[4 * q + 3] = __uint_as_float(v0[4 * q + 3]) + b4[q].w;
-              h[32 + 4 * q] = __uint_as_float(v1[4 * q]) + b4[8 + q].x;
-              h[32 + 4 * q + 1] = __uint_as_float(v1[4 * q + 1]) + b4[8 + q].y;
-              h[32 + 4 * q + 2] = __uint_as_float(v1[4 * q + 2]) + b4[8 + q].z;
-              h[32 + 4 * q + 3] = __uint_as_float(v1[4 * q + 3]) + b4[8 + q].w;
+            for (int j = 0; j < 8; ++j) {
+              h[4 * j] = __uint_as_float(v[4 * j]) + b4[j].x;
+              h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4[j].y;
+              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4[j].z;
+              h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4[j].w;
             }
             if (s == 7) {                              // alpha_linear on the fp32 activations (run_nerf_helpers.py:110)
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(sd->w_alpha + c * 64) + q);
-                sig_acc = fmaf(fmaxf(h[4 * q], 0.f), w4.x, sig_acc);
-                sig_acc = fmaf(fmaxf(h[4 * q + 1], 0.f), w4.y, sig_acc);
-                sig_acc = fmaf(fmaxf(h[4 * q + 2], 0.f), w4.z, sig_acc);
-                sig_acc = fmaf(fmaxf(h[4 * q + 3], 0.f), w4.w, sig_acc);
+              for (int j = 0; j < 8; ++j) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(sd->w_alpha + col0) + j);
+                sig_acc = fmaf(fmaxf(h[4 * j], 0.f), w4.x, sig_acc);
+                sig_acc = fmaf(fmaxf(h[4 * j + 1], 0.f), w4.y, sig_acc);
+                sig_acc = fmaf(fmaxf(h[4 * j + 2], 0.f), w4.z, sig_acc);
+                sig_acc = fmaf(fmaxf(h[4 * j + 3], 0.f), w4.w, sig_acc);
               }
             }
             if (last && a.dbg) {
               if (live) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  float4 o = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+                for (int j = 0; j < 8; ++j) {
+                  float4 o = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
                   if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                  reinterpret_cast<float4*>(a.dbg + m * 256 + c * 64)[q] = o;
+                  reinterpret_cast<float4*>(a.dbg + m * 256 + col0)[j] = o;
                 }
               }
             } else {
-              const uint32_t cb = act + c * CHUNK_BYTES;
+              const uint32_t cb = act + (col0 >> 6) * CHUNK_BYTES;     // activation K-chunk holding these columns
+              const int u0 = (col0 & 63) >> 3;                         // first 16-byte unit inside the 128-byte row
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const uint32_t addr = cb + row * 128 + (((u ^ (row & 7)) & 7) << 4);
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t addr = cb + row * 128 + ((((u0 + u) ^ (row & 7)) & 7) << 4);
                 if (relu)
                   st_shared_v4(addr, pack_bf16_relu(h[8 * u], h[8 * u + 1]), pack_bf16_relu(h[8 * u + 2], h[8 * u + 3]),
                                pack_bf16_relu(h[8 * u + 4], h[8 * u + 5]), pack_bf16_relu(h[8 * u + 6], h[8 * u + 7]));
@@ -704,44 +715,57 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
               }
             }
           }
-          if (s == 7) sigma = sig_acc + __ldg(&sd->b_alpha);
-          if (s == 8) {                                // the PE chunk is free since step 5 retired: view-direction features
+          if (s == 7) {
+            // combine the two column halves of sigma: the PE chunk is free between step 5 (last reader) and step 8
+            if (hcol == 1) scratch_pe[row] = sig_acc;
+            pair_sync();
+            if (hcol == 0) sigma = sig_acc + scratch_pe[row] + __ldg(&sd->b_alpha);
+            pair_sync();
+          }
+          if (s == 8 && hcol == 0) {                   // view-direction features into the (free) PE chunk
             float f[64];
             encode3<L_DIR>(vx, vy, vz, f);
             store_row_chunk(pe, row, f);
           }
           if (!last) signal_a_ready();
-          if (tracing && (warp & 3) == 2) trace_evt(2, 0x4000 | (s << 4) | g, clock64(), clock64(), 0);
+          if (tracing && e == 0) trace_evt(2, 0x4000 | (s << 4) | g, clock64(), clock64(), 0);
         } else {
-          // ---- views layer epilogue: relu(acc + b) . w_rgb -> raw ----
+          // ---- views layer epilogue: relu(acc + b) . w_rgb -> raw; this thread covers 64 of the 128 columns ----
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {                // 32 columns at a time
-            uint32_t v0[32];
-            tmem_ld32(tmem_row + c * 32, v0);
+          for (int cc = 0; cc < 2; ++cc) {
+            const int col0 = hcol * 64 + cc * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem_row + col0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(sd->bias_views + c * 32) + q);
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[0] + c * 32) + q);
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[1] + c * 32) + q);
-              const float4 w2 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[2] + c * 32) + q);
-              const float h0 = fmaxf(__uint_as_float(v0[4 * q]) + b4.x, 0.f);
-              const float h1 = fmaxf(__uint_as_float(v0[4 * q + 1]) + b4.y, 0.f);
-              const float h2 = fmaxf(__uint_as_float(v0[4 * q + 2]) + b4.z, 0.f);
-              const float h3 = fmaxf(__uint_as_float(v0[4 * q + 3]) + b4.w, 0.f);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(sd->bias_views + col0) + j);
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[0] + col0) + j);
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[1] + col0) + j);
+              const float4 w2 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[2] + col0) + j);
+              const float h0 = fmaxf(__uint_as_float(v[4 * j]) + b4.x, 0.f);
+              const float h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + b4.y, 0.f);
+              const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + b4.z, 0.f);
+              const float h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + b4.w, 0.f);
               r0 = fmaf(h0, w0.x, r0); r0 = fmaf(h1, w0.y, r0); r0 = fmaf(h2, w0.z, r0); r0 = fmaf(h3, w0.w, r0);
               r1 = fmaf(h0, w1.x, r1); r1 = fmaf(h1, w1.y, r1); r1 = fmaf(h2, w1.z, r1); r1 = fmaf(h3, w1.w, r1);
               r2 = fmaf(h0, w2.x, r2); r2 = fmaf(h1, w2.y, r2); r2 = fmaf(h2, w2.z, r2); r2 = fmaf(h3, w2.w, r2);
               if (a.dbg && live) {
-                reinterpret_cast<float4*>(a.dbg + m * 256 + c * 32)[q] = make_float4(h0, h1, h2, h3);
+                reinterpret_cast<float4*>(a.dbg + m * 256 + col0)[j] = make_float4(h0, h1, h2, h3);
               }
             }
           }
-          if (live) {
-            const float4 o = make_float4(r0 + __ldg(&sd->b_rgb[0]), r1 + __ldg(&sd->b_rgb[1]), r2 + __ldg(&sd->b_rgb[2]), sigma);
+          // combine the halves through the slot's activation buffer (free: every MMA of this tile has retired)
+          if (hcol == 1) { scratch_act[row * 4] = r0; scratch_act[row * 4 + 1] = r1; scratch_act[row * 4 + 2] = r2; }
+          pair_sync();
+          if (hcol == 0 && live) {
+            const float4 o = make_float4(r0 + scratch_act[row * 4] + __ldg(&sd->b_rgb[0]),
+                                         r1 + scratch_act[row * 4 + 1] + __ldg(&sd->b_rgb[1]),
+                                         r2 + scratch_act[row * 4 + 2] + __ldg(&sd->b_rgb[2]), sigma);
             st_stream4(reinterpret_cast<float4*>(a.raw) + m, o);
           }
+          pair_sync();                                   // scratch is re-used as the A operand of the next tile
         }
       }
       // the accumulator has been drained (tcgen05.wait::ld above); signal_a_ready() of the next unit orders it
