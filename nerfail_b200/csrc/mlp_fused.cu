@@ -20,6 +20,7 @@
 // Activations never leave the SM; HBM traffic is 16 B read + 16 B written per sample.
 #include "common.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace nfb {
 
@@ -53,8 +54,9 @@ constexpr int SM_ACT = 0;                                   // [2 slots][4 chunk
 constexpr int SM_PE = SM_ACT + 2 * 4 * CHUNK_BYTES;         // [2 slots][16 KB]
 constexpr int SM_W = SM_PE + 2 * CHUNK_BYTES;               // [NSTAGE][16 KB]
 constexpr int SM_BAR = SM_W + NSTAGE * CHUNK_BYTES;         // barriers + tmem pointer
-constexpr int SM_TOTAL = SM_BAR + 256;
-constexpr int SMEM_BYTES = SM_TOTAL + 1024;                 // slack for manual 1024-byte alignment
+constexpr int SM_BIAS = SM_BAR + 256;                        // [2 slots][256 floats]: bias row of the step being drained
+constexpr int SM_TOTAL = SM_BIAS + 2 * 256 * 4;
+constexpr int SMEM_BYTES = SM_TOTAL;                        // the dynamic window starts 1024-byte aligned (checked in-kernel)
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 // fp32 side parameters (biases and the two small heads evaluated on CUDA cores), device resident
@@ -68,11 +70,18 @@ struct MlpSide {
   float b_rgb[3];
 };
 
+// The epilogues read biases / head weights warp-uniformly.  With ~225 KB of shared memory per CTA the L1 carve-out is
+// a few KB, so global loads of these 12 KB per network miss L1 and cost an L2 round trip per 32 columns (measured: 900
+// cycles per 32-column epilogue iteration).  They live in constant memory instead: up to MAX_NETS networks per device.
+constexpr int MAX_NETS = 4;
+__constant__ MlpSide c_side[MAX_NETS];
+
 }  // namespace nfb
 
 struct nfb_mlp {
   __nv_bfloat16* image;      // TOTAL_BLOCKS x 16 KB pre-swizzled weight blocks
-  nfb::MlpSide* side;
+  nfb::MlpSide* side;        // staging copy in global memory (written by the pack kernel)
+  int cslot;                 // index into the __constant__ c_side table of this device
   int* abort_flag;           // set by the kernel if a barrier wait timed out
   int device;
   int64_t n_params;
@@ -324,7 +333,8 @@ __device__ __forceinline__ void store_row_chunk(uint32_t chunk_base, int row, co
 
 struct FwdArgs {
   const __nv_bfloat16* image;
-  const MlpSide* side;
+  const MlpSide* side;      // global copy (bias rows are staged from here into shared memory)
+  int cslot;                // index into c_side (constant memory): head weights read through the uniform datapath
   int* abort_flag;
   int mode;                 // 0: explicit pts + dirs, 1: rays + z_vals
   const float* pts;         // [M,3]
@@ -403,8 +413,8 @@ __device__ __forceinline__ uint32_t a_chunk_addr(int s, int c, uint32_t act, uin
 template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_fused_fwd_kernel(const FwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);          // swizzled operands need a 1024-byte aligned window
   const uint32_t bar0 = base + SM_BAR;
   auto W_FULL = [&](int s) { return bar0 + 8 * s; };
   auto W_EMPTY = [&](int s) { return bar0 + 8 * (NSTAGE + s); };
@@ -413,11 +423,13 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
   const uint32_t tmem_slot = bar0 + 8 * (2 * NSTAGE + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + SM_BAR + 8 * (2 * NSTAGE + 4));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);   // broadcast => warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   volatile int* abort_flag = a.abort_flag;
   const int nsteps = a.nsteps;
+  if ((base & 1023u) != 0u && threadIdx.x == 0) *abort_flag = 1;   // misaligned window: results would be garbage
   const bool tracing = a.trace != nullptr && blockIdx.x == 0;
   int trace_n = 0;
   auto trace_evt = [&](int role, unsigned long long tag, unsigned long long t0, unsigned long long t1, unsigned long long aux) {
@@ -610,7 +622,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
     const uint32_t pe = base + SM_PE + g * CHUNK_BYTES;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(q << 5) << 16) + g * 256;
     const uint32_t pair_bar = 1 + g * 4 + q;          // named barrier shared by the two warps of a (slot, quarter)
-    const MlpSide* __restrict__ sd = a.side;
+    const MlpSide* __restrict__ sd = &c_side[a.cslot];
     uint32_t full_phase = 0;
     auto signal_a_ready = [&]() {                     // this warp's part of the A operand is in shared memory
       tc_fence_before();
@@ -624,6 +636,22 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
     // shared-memory scratch (generic proxy) used to combine the two column halves of a row
     float* scratch_pe = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + SM_PE + g * CHUNK_BYTES);
     float* scratch_act = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + SM_ACT + g * 4 * CHUNK_BYTES);
+    // Bias staging: per-thread broadcast loads of the bias (global or constant memory) cost 2-4x the rest of a
+    // 32-column epilogue iteration (scripts/ubench/epilogue.cu), so the 256 threads of a slot keep the bias row of
+    // the step being drained in shared memory (read back as broadcast LDS.128) and refill it once per step with
+    // the next step's row, prefetched into a register while the accumulator is drained.
+    float* bias_s = reinterpret_cast<float*>(smem_raw + SM_BIAS) + g * 256;
+    const int tslot = ((e & 7) << 5) + lane;          // 0..255 within the slot
+    const uint32_t slot_bar = 9 + g;                  // named barrier of the slot's 8 epilogue warps
+    auto slot_sync = [&]() { asm volatile("bar.sync %0, 256;" :: "r"(slot_bar) : "memory"); };
+    const MlpSide* __restrict__ sg = a.side;
+    auto bias_elem = [&](int step) -> float {         // element `tslot` of the bias row used by MMA step `step`
+      if (step < 8) return __ldg(&sg->bias[step][tslot]);
+      if (step == 8) return __ldg(&sg->bias_feat[tslot]);
+      return tslot < 128 ? __ldg(&sg->bias_views[tslot]) : 0.f;
+    };
+    bias_s[tslot] = bias_elem(0);
+    slot_sync();
 
     for (int64_t unit = group; unit < nunits; unit += ngroups) {
       const int64_t m = unit * ROWS_PER_UNIT + (int64_t)g * (TILE_M * CG) + rank * TILE_M + row;
@@ -660,8 +688,8 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
         full_phase ^= 1;
         tc_fence_after();
         const bool last = (s == nsteps - 1);
+        const float next_bias = bias_elem(last ? 0 : s + 1);      // consumed after this step's drain (latency hidden)
         if (s < 9) {
-          const float* __restrict__ bias = (s < 8) ? sd->bias[s] : sd->bias_feat;
           const bool relu = (s < 8);
           float sig_acc = 0.f;
 #pragma unroll 1
@@ -671,7 +699,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             tmem_ld32(tmem_row + col0, v);
             float4 b4[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
+            for (int j = 0; j < 8; ++j) b4[j] = reinterpret_cast<const float4*>(bias_s + col0)[j];
             tmem_ld_wait();
             float h[32];
 #pragma unroll
@@ -684,7 +712,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             if (s == 7) {                              // alpha_linear on the fp32 activations (run_nerf_helpers.py:110)
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(sd->w_alpha + col0) + j);
+                const float4 w4 = reinterpret_cast<const float4*>(sd->w_alpha + col0)[j];
                 sig_acc = fmaf(fmaxf(h[4 * j], 0.f), w4.x, sig_acc);
                 sig_acc = fmaf(fmaxf(h[4 * j + 1], 0.f), w4.y, sig_acc);
                 sig_acc = fmaf(fmaxf(h[4 * j + 2], 0.f), w4.z, sig_acc);
@@ -719,7 +747,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             // combine the two column halves of sigma: the PE chunk is free between step 5 (last reader) and step 8
             if (hcol == 1) scratch_pe[row] = sig_acc;
             pair_sync();
-            if (hcol == 0) sigma = sig_acc + scratch_pe[row] + __ldg(&sd->b_alpha);
+            if (hcol == 0) sigma = sig_acc + scratch_pe[row] + sd->b_alpha;
             pair_sync();
           }
           if (s == 8 && hcol == 0) {                   // view-direction features into the (free) PE chunk
@@ -727,6 +755,11 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             encode3<L_DIR>(vx, vy, vz, f);
             store_row_chunk(pe, row, f);
           }
+          if (tracing && e == 0) trace_evt(2, 0x6000 | (s << 4) | g, clock64(), clock64(), 2);
+          slot_sync();                                 // every warp of the slot has read this step's bias row
+          bias_s[tslot] = next_bias;
+          slot_sync();
+          if (tracing && e == 0) trace_evt(2, 0x6800 | (s << 4) | g, clock64(), clock64(), 2);
           if (!last) signal_a_ready();
           if (tracing && e == 0) trace_evt(2, 0x4000 | (s << 4) | g, clock64(), clock64(), 0);
         } else {
@@ -740,10 +773,10 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(sd->bias_views + col0) + j);
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[0] + col0) + j);
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[1] + col0) + j);
-              const float4 w2 = __ldg(reinterpret_cast<const float4*>(sd->w_rgb[2] + col0) + j);
+              const float4 b4 = reinterpret_cast<const float4*>(bias_s + col0)[j];
+              const float4 w0 = reinterpret_cast<const float4*>(sd->w_rgb[0] + col0)[j];
+              const float4 w1 = reinterpret_cast<const float4*>(sd->w_rgb[1] + col0)[j];
+              const float4 w2 = reinterpret_cast<const float4*>(sd->w_rgb[2] + col0)[j];
               const float h0 = fmaxf(__uint_as_float(v[4 * j]) + b4.x, 0.f);
               const float h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + b4.y, 0.f);
               const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + b4.z, 0.f);
@@ -760,12 +793,15 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
           if (hcol == 1) { scratch_act[row * 4] = r0; scratch_act[row * 4 + 1] = r1; scratch_act[row * 4 + 2] = r2; }
           pair_sync();
           if (hcol == 0 && live) {
-            const float4 o = make_float4(r0 + scratch_act[row * 4] + __ldg(&sd->b_rgb[0]),
-                                         r1 + scratch_act[row * 4 + 1] + __ldg(&sd->b_rgb[1]),
-                                         r2 + scratch_act[row * 4 + 2] + __ldg(&sd->b_rgb[2]), sigma);
+            const float4 o = make_float4(r0 + scratch_act[row * 4] + sd->b_rgb[0],
+                                         r1 + scratch_act[row * 4 + 1] + sd->b_rgb[1],
+                                         r2 + scratch_act[row * 4 + 2] + sd->b_rgb[2], sigma);
             st_stream4(reinterpret_cast<float4*>(a.raw) + m, o);
           }
           pair_sync();                                   // scratch is re-used as the A operand of the next tile
+          slot_sync();
+          bias_s[tslot] = next_bias;                     // bias row of step 0 for the next unit
+          slot_sync();
         }
       }
       // the accumulator has been drained (tcgen05.wait::ld above); signal_a_ready() of the next unit orders it
@@ -789,6 +825,21 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
 // ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_slot_mutex;
+unsigned g_slot_used[64] = {0};      // per device: bitmap of c_side entries in use
+int acquire_cslot(int device) {
+  std::lock_guard<std::mutex> lock(g_slot_mutex);
+  for (int i = 0; i < nfb::MAX_NETS; ++i)
+    if (!(g_slot_used[device] & (1u << i))) { g_slot_used[device] |= 1u << i; return i; }
+  return -1;
+}
+void release_cslot(int device, int slot) {
+  std::lock_guard<std::mutex> lock(g_slot_mutex);
+  if (slot >= 0) g_slot_used[device] &= ~(1u << slot);
+}
+}  // namespace
+
 extern "C" {
 
 int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_views, int skip) {
@@ -798,9 +849,17 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
                      "mlp_create: fused kernel is built for D=8 W=256 input_ch=63 input_ch_views=27 skips=[4] "
                      "(got D=%d W=%d input_ch=%d input_ch_views=%d skip=%d)", D, W, input_ch, input_ch_views, skip);
   nfb_mlp* h = new nfb_mlp();
-  h->image = nullptr; h->side = nullptr; h->abort_flag = nullptr;
+  h->image = nullptr; h->side = nullptr; h->abort_flag = nullptr; h->cslot = -1;
   h->n_params = nfb::param_layout().total;
   cudaError_t e = cudaGetDevice(&h->device);
+  if (e == cudaSuccess && (h->device < 0 || h->device >= 64)) { delete h; return nfb::fail(NFB_E_UNSUPPORTED, "mlp_create: device index out of range"); }
+  if (e == cudaSuccess) {
+    h->cslot = acquire_cslot(h->device);
+    if (h->cslot < 0) {
+      delete h;
+      return nfb::fail(NFB_E_UNSUPPORTED, "mlp_create: at most %d fused networks per device may be alive at once", nfb::MAX_NETS);
+    }
+  }
   if (e == cudaSuccess) e = cudaMalloc(&h->image, (size_t)nfb::TOTAL_BLOCKS * nfb::CHUNK_BYTES);
   if (e == cudaSuccess) e = cudaMalloc(&h->side, sizeof(nfb::MlpSide));
   if (e == cudaSuccess) e = cudaMalloc(&h->abort_flag, sizeof(int));
@@ -811,6 +870,7 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
     e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e != cudaSuccess) {
     cudaFree(h->image); cudaFree(h->side); cudaFree(h->abort_flag);
+    release_cslot(h->device, h->cslot);
     delete h;
     return nfb::fail(NFB_E_CUDA, "mlp_create: %s", cudaGetErrorString(e));
   }
@@ -824,12 +884,18 @@ int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* st
   NFB_REQUIRE(h && params, "mlp_update: null pointer");
   NFB_REQUIRE(n_params == h->n_params, "mlp_update: expected %lld parameters, got %lld", (long long)h->n_params, (long long)n_params);
   nfb::pack_weights_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image, h->side);
-  return nfb::check_launch("mlp_update");
+  int rc = nfb::check_launch("mlp_update");
+  if (rc) return rc;
+  // stream-ordered device-to-device copy of the fp32 side parameters into this network's constant-memory entry
+  NFB_CUDA(cudaMemcpyToSymbolAsync(nfb::c_side, h->side, sizeof(nfb::MlpSide), (size_t)h->cslot * sizeof(nfb::MlpSide),
+                                   cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return NFB_OK;
 }
 
 int nfb_mlp_destroy(nfb_mlp_t* h) {
   if (!h) return NFB_OK;
   cudaFree(h->image); cudaFree(h->side); cudaFree(h->abort_flag);
+  release_cslot(h->device, h->cslot);
   delete h;
   return NFB_OK;
 }
@@ -856,7 +922,7 @@ static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const floa
   NFB_REQUIRE(nsteps >= 1 && nsteps <= nfb::NSTEP && (nsteps == nfb::NSTEP || dbg), "mlp_fwd: bad nsteps");
   if (R == 0) return NFB_OK;
   nfb::FwdArgs a;
-  a.image = h->image; a.side = h->side; a.abort_flag = h->abort_flag;
+  a.image = h->image; a.side = h->side; a.cslot = h->cslot; a.abort_flag = h->abort_flag;
   a.mode = mode; a.pts = pts; a.dirs = dirs; a.rays = rays; a.z_vals = z_vals;
   a.M = (int64_t)R * S; a.S = S; a.raw = raw; a.nsteps = nsteps; a.dbg = dbg; a.trace = trace;
   // NERFAIL_B200_CG=1 selects the single-CTA variant (cta_group::1); default is the CTA-pair kernel (cta_group::2).

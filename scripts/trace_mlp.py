@@ -50,3 +50,20 @@ for (tag, b, en) in acc:
             d.append(ts - en); break
 if d:
     print(f"epilogue duration (ACC_FULL observed -> A_READY signalled): median {np.median(d):.0f} cycles, max {max(d)}")
+# per-step epilogue phases of warp 2 (slot 0): ACC_FULL observed -> drain loop done -> bias refilled (2 slot barriers) -> A_READY signalled
+ev = [(int(x[0]), int(x[1]), int(x[2])) for x in epi]
+rows = []
+for i, (tag, b, en) in enumerate(ev):
+    if (tag & 0xF000) == 0x3000 and ((tag >> 4) & 0xFF) < 9:
+        key = tag & 0xFFF
+        t_acc = en; d = {}
+        for (tg, b2, e2) in ev[i + 1:i + 5]:
+            if (tg & 0xFFF) != key: continue
+            if (tg & 0xF800) == 0x6000: d["drain"] = b2 - t_acc
+            elif (tg & 0xF800) == 0x6800: d["refill"] = b2 - t_acc
+            elif (tg & 0xF000) == 0x4000: d["signal"] = b2 - t_acc
+        if len(d) == 3: rows.append((en - b, d["drain"], d["refill"], d["signal"]))
+rows = np.array(rows)
+if len(rows):
+    print("epilogue phases, median cycles after ACC_FULL: drain loop done %d, bias refilled %d, signalled %d; wait for ACC_FULL %d (n=%d)" %
+          (np.median(rows[:, 1]), np.median(rows[:, 2]), np.median(rows[:, 3]), np.median(rows[:, 0]), len(rows)))
