@@ -274,6 +274,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     import nerfail_b200 as nb
@@ -400,7 +402,11 @@ def main():
                     "api": "nerfail_b200.render(H, W, K, chunk=1024, c2w=<host pose>) + rgb/disp/acc to pinned host memory"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "nfb::mlp_fused_fwd_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_v3_cta_group2.md (199.5 MB for 12.58 M
+                         # samples = 15.86 B/sample; algorithmic 20 B/sample) scaled to this run's average launch
+                         "traffic": 15.86 * (mlp_flop / FLOP_PER_SAMPLE) / max(1, n_mlp_launches),
+                         "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_v3_cta_group2.md)",
                          "peak_source": f"{how} bf16_tflops_sustained", "launches": n_mlp_launches,
                          "avg_launch_ms": mlp_ms / max(1, n_mlp_launches),
                          "algorithmic_flop_per_sample": FLOP_PER_SAMPLE, "share_of_step": mlp_ms / ms},
