@@ -6,6 +6,7 @@
 // streaming operands (weights, indices, original image, outputs) are read/written exactly once with
 // 128-bit accesses.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nfb {
 
@@ -137,9 +138,10 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
                :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// One thread per pixel computes G = dL/dx (4 channels); the 8 contributions w_k * G go to table rows idx_k.
-// Lanes of a warp that hit the same row at the same k are merged (match.any) and only the lowest lane issues
-// the 128-bit reduction, so neighbouring pixels that share neighbours cost one L2 atomic instead of several.
+// One thread per pixel computes G = dL/dx (4 channels); the 8 contributions w_k * G go to table rows idx_k as
+// 128-bit L2 reductions.  AGGREGATE = true first merges lanes of the warp that hit the same row at the same k
+// (match.any) so that only the lowest lane issues the reduction; kept selectable, off by default (see the launcher).
+template <bool AGGREGATE>
 __global__ void __launch_bounds__(256)
 gauss_scatter_bwd_kernel(const float4* __restrict__ g_x, const float4* __restrict__ g_xrgba,
                          const float4* __restrict__ x_saved, const float* __restrict__ w_idx,
@@ -184,17 +186,21 @@ gauss_scatter_bwd_kernel(const float4* __restrict__ g_x, const float4* __restric
       int id = px.idx[k];
       if (live) id = id < 0 ? 0 : (id >= T ? (int)(T - 1) : id);
       float4 v = make_float4(G.x * px.w[k], G.y * px.w[k], G.z * px.w[k], G.w * px.w[k]);
-      const unsigned peers = __match_any_sync(FULL, id);
-      const int leader = __ffs(peers) - 1;
-      unsigned rem = peers & ~(1u << leader);
-      while (__any_sync(FULL, rem != 0)) {
-        const int src = rem ? (__ffs(rem) - 1) : lane;
-        const float ox = __shfl_sync(FULL, v.x, src), oy = __shfl_sync(FULL, v.y, src);
-        const float oz = __shfl_sync(FULL, v.z, src), ow = __shfl_sync(FULL, v.w, src);
-        if (lane == leader && rem) { v.x += ox; v.y += oy; v.z += oz; v.w += ow; }
-        rem &= rem - 1;
+      if (AGGREGATE) {
+        const unsigned peers = __match_any_sync(FULL, id);
+        const int leader = __ffs(peers) - 1;
+        unsigned rem = peers & ~(1u << leader);
+        while (__any_sync(FULL, rem != 0)) {
+          const int src = rem ? (__ffs(rem) - 1) : lane;
+          const float ox = __shfl_sync(FULL, v.x, src), oy = __shfl_sync(FULL, v.y, src);
+          const float oz = __shfl_sync(FULL, v.z, src), ow = __shfl_sync(FULL, v.w, src);
+          if (lane == leader && rem) { v.x += ox; v.y += oy; v.z += oz; v.w += ow; }
+          rem &= rem - 1;
+        }
+        if (live && lane == leader) red_add_v4(g_table + id, v);
+      } else {
+        if (live) red_add_v4(g_table + id, v);
       }
-      if (live && lane == leader) red_add_v4(g_table + id, v);
     }
   }
 }
@@ -244,9 +250,19 @@ int nfb_gauss_scatter_bwd(const float* g_x, const float* g_xrgba, const float* x
                 reinterpret_cast<uintptr_t>(g_xrgba) | reinterpret_cast<uintptr_t>(x)) & 15) == 0,
               "gauss_scatter_bwd: buffers must be 16-byte aligned");
   if (B * HW == 0) return NFB_OK;
-  nfb::gauss_scatter_bwd_kernel<<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(g_x), reinterpret_cast<const float4*>(g_xrgba),
-      reinterpret_cast<const float4*>(x), w_idx, ori, B, HW, eps, T, reinterpret_cast<float4*>(g_table));
+  // Default: every lane issues its own red.global.add.v4.f32.  NERFAIL_B200_SCATTER_AGG=1 enables the warp-level
+  // merge of equal rows (match.any + shuffle tree).  Measured on B200 at 800x800, P=3 (scripts/profile_gauss.py):
+  // aggregated 64-73 us per view vs 42-47 us plain for clustered, 3x3-shared and uniformly random indices alike -
+  // the L2 atomic units absorb the duplicates faster than 8 match.any rounds per pixel can remove them.
+  static const bool agg = []() { const char* e = getenv("NERFAIL_B200_SCATTER_AGG"); return e && e[0] == '1'; }();
+  if (agg)
+    nfb::gauss_scatter_bwd_kernel<true><<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(g_x), reinterpret_cast<const float4*>(g_xrgba),
+        reinterpret_cast<const float4*>(x), w_idx, ori, B, HW, eps, T, reinterpret_cast<float4*>(g_table));
+  else
+    nfb::gauss_scatter_bwd_kernel<false><<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(g_x), reinterpret_cast<const float4*>(g_xrgba),
+        reinterpret_cast<const float4*>(x), w_idx, ori, B, HW, eps, T, reinterpret_cast<float4*>(g_table));
   return nfb::check_launch("gauss_scatter_bwd");
 }
 
