@@ -123,6 +123,20 @@ NFB_API int nfb_linear_bwd_weight(const float* dY, int lddy, const float* Y, int
                           float* workspace, int64_t workspace_bytes, void* stream);
 NFB_API int64_t nfb_linear_bwd_weight_workspace(int64_t M, int N, int K);
 
+/* bf16 tensor-core weight gradient over "tile images" (per 128-row tile: 64-column chunks of 128 rows x 128 bytes with
+ * the 128-byte swizzle, i.e. the layout the fused kernels use for their MMA operands and leave in HBM when training).
+ * replaces: the wgrad GEMMs of loss.backward() (run_nerf.py:791) for one layer:
+ *   dW[n, k] = sum_rows dY[row, n] * X[row, k],   db[n] = sum_rows dY[row, n]
+ * dy: ndy in {2,4} chunks per tile (n = 64*ndy), x: nx in {1,2,4} chunks (k = 64*nx); *_tile_pitch = bytes between tiles.
+ * Each of nfb_wgrad_parts() CTAs writes a partial: part_w [parts][64*ndy][64*nx], part_b [parts][64*ndy] (or NULL);
+ * nfb_wgrad_reduce sums partials in a fixed order into out[r*ld + col0 + c] for c < cols_valid.  status: device int
+ * that the kernel raises if a pipeline barrier timed out.                                                          */
+NFB_API int nfb_wgrad_parts(void);
+NFB_API int nfb_wgrad_bf16(const void* dy, int64_t dy_tile_pitch, int ndy, const void* x, int64_t x_tile_pitch, int nx,
+                           int64_t ntiles, float* part_w, float* part_b, int* status, void* stream);
+NFB_API int nfb_wgrad_reduce(const float* part, int nparts, int rows, int cols, int cols_valid, float* out, int ld, int col0,
+                             int accumulate, void* stream);
+
 /* Alpha compositing. replaces: run_nerf.py:262-305 (raw2outputs) and, when pts_max != NULL,
  * nerf_to_coord.py:418-421 (arg-max-weight point o + d*z[argmax], first maximum wins).
  * raw [R,S,4], z_vals [R,S], rays_d [R,3] (taken from rays+3 with pitch ray_pitch floats), noise [R,S] or NULL.

@@ -464,3 +464,45 @@ class GaussGatherFn(torch.autograd.Function):
             return None, None, None, None, None
         g = _GaussScatterFn.apply(g_x, g_xrgba, x, w_idx, ori_u8, ctx.eps, ctx.table_shape)
         return g, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tile images + tensor-core weight gradient
+# ------------------------------------------------------------------------------------------------
+def to_tile_image(x: torch.Tensor) -> torch.Tensor:
+    """[M, C] (M % 128 == 0, C % 64 == 0) -> bf16 tile image [M/128, C/64, 128, 64] with the 128-byte swizzle
+    (16-byte unit u of row r is stored at unit u ^ (r % 8)); test / interchange helper, pure indexing."""
+    M, Cc = x.shape
+    assert M % 128 == 0 and Cc % 64 == 0
+    t = x.to(torch.bfloat16).reshape(M // 128, 128, Cc // 64, 8, 8).permute(0, 2, 1, 3, 4)      # tile, chunk, row, unit, elem
+    r = torch.arange(128, device=x.device).reshape(1, 1, 128, 1, 1)
+    u = torch.arange(8, device=x.device).reshape(1, 1, 1, 8, 1)
+    src_unit = (u ^ (r & 7)).expand(t.shape[0], t.shape[1], 128, 8, 8)
+    out = torch.gather(t, 3, src_unit)          # out[.., r, p, :] = t[.., r, p ^ (r&7), :]  (XOR is an involution)
+    return out.reshape(M // 128, Cc // 64, 128, 64).contiguous()
+
+
+def wgrad_bf16(dy_img: torch.Tensor, x_img: torch.Tensor, want_bias=True):
+    """dy_img [T, ndy, 128, 64] bf16, x_img [T, nx, 128, 64] bf16 (tile images; may be views with a tile pitch) ->
+    (dW [64*ndy, 64*nx] fp32, db [64*ndy] fp32 or None)."""
+    lib = _lib.load()
+    T, ndy = dy_img.shape[0], dy_img.shape[1]
+    nx = x_img.shape[1]
+    assert dy_img.dtype == torch.bfloat16 and x_img.dtype == torch.bfloat16 and x_img.shape[0] == T
+    assert dy_img.stride(1) == 8192 and x_img.stride(1) == 8192 and dy_img.stride(3) == 1 and x_img.stride(3) == 1
+    dev = dy_img.device
+    parts = int(lib.nfb_wgrad_parts())
+    pw = torch.empty((parts, 64 * ndy, 64 * nx), dtype=torch.float32, device=dev)
+    pb = torch.empty((parts, 64 * ndy), dtype=torch.float32, device=dev) if want_bias else None
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    dW = torch.empty((64 * ndy, 64 * nx), dtype=torch.float32, device=dev)
+    db = torch.empty((64 * ndy,), dtype=torch.float32, device=dev) if want_bias else None
+    with torch.cuda.device(dev):
+        check(lib.nfb_wgrad_bf16(dy_img.data_ptr(), dy_img.stride(0) * 2, ndy, x_img.data_ptr(), x_img.stride(0) * 2, nx, T,
+                                 ptr(pw), ptr(pb), ptr(status), stream()), "nfb_wgrad_bf16")
+        check(lib.nfb_wgrad_reduce(ptr(pw), parts, 64 * ndy, 64 * nx, 64 * nx, ptr(dW), 64 * nx, 0, 0, stream()), "nfb_wgrad_reduce")
+        if want_bias:
+            check(lib.nfb_wgrad_reduce(ptr(pb), parts, 1, 64 * ndy, 64 * ndy, ptr(db), 64 * ndy, 0, 0, stream()), "nfb_wgrad_reduce")
+    if int(status.item()) != 0:
+        raise RuntimeError("nfb_wgrad_bf16: pipeline barrier timed out")
+    return dW, db

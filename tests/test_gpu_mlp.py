@@ -167,3 +167,20 @@ def test_training_step_gradients_vs_reference_golden(cuda):
                 checked += 1
         assert (num / den) ** 0.5 <= 1.5e-3, (tag, (num / den) ** 0.5)
     assert checked >= 12
+
+
+@pytest.mark.parametrize("ntiles,ndy,nx", [(1, 4, 4), (3, 4, 4), (5, 2, 4), (7, 4, 1), (300, 4, 4), (301, 2, 2)])
+def test_wgrad_bf16_tile_images(cuda, ntiles, ndy, nx):
+    """tcgen05 weight-gradient GEMM with MN-major operands read straight from the swizzled tile images:
+    dW = dY^T X and db = column sums, against an fp64 product of the same bf16-rounded operands."""
+    from nerfail_b200 import ops
+    g = torch.Generator().manual_seed(ntiles * 100 + ndy * 10 + nx)
+    M = ntiles * 128
+    dy = (torch.randn(M, 64 * ndy, generator=g) * 0.5).to(torch.bfloat16)
+    x = torch.relu(torch.randn(M, 64 * nx, generator=g)).to(torch.bfloat16)
+    dW, db = ops.wgrad_bf16(ops.to_tile_image(dy.float().to(cuda)), ops.to_tile_image(x.float().to(cuda)))
+    ref_w = dy.double().t() @ x.double()
+    ref_b = dy.double().sum(0)
+    scale = float(ref_w.abs().max())
+    assert float((dW.cpu().double() - ref_w).abs().max()) < 2e-5 * scale * max(1.0, ntiles ** 0.5) + 1e-4, "dW"
+    assert float((db.cpu().double() - ref_b).abs().max()) < 1e-4 * float(ref_b.abs().max()) + 1e-3, "db"
