@@ -96,6 +96,19 @@ NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, co
                       const float* rays, const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg,
                       void* stream);
 
+/* Training on tensor cores (bf16 operands, fp32 accumulate).
+ * replaces: NeRF.forward under autograd + the data-gradient half of loss.backward() (run_nerf.py:776-791).
+ * nfb_mlp_fwd_train = nfb_mlp_fwd (mode 1) that also leaves, per 128-row tile, every layer's bf16 activation as a tile
+ * image act_img [tiles][40][16 KB] and the relu masks as bit words mask [tiles][9][128][8] (layout: csrc/mlp_train.inl).
+ * nfb_mlp_bwd_data runs the data-gradient chain from g_raw [M,4] (d loss / d raw) and leaves every layer's dY as a tile
+ * image dy_img [tiles][38][16 KB]; the weight gradients are then nfb_wgrad_bf16 products of the two images.
+ * tiles = nfb_mlp_train_tiles(M).                                                                                   */
+NFB_API int64_t nfb_mlp_train_tiles(int64_t M);
+NFB_API int nfb_mlp_fwd_train(const nfb_mlp_t* h, const float* rays, const float* z_vals, int R, int S, float* raw,
+                              void* act_img, uint32_t* mask, void* stream);
+NFB_API int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_t* mask, void* dy_img,
+                             void* stream);
+
 /* Profiling aid: the full forward (mode 1) while CTA 0 records a timeline of its barrier waits into
  * trace [3 roles][2048 events][4] uint64 = (tag, clock begin, clock end, aux); roles: 0 weight producer, 1 MMA warp,
  * 2 epilogue warps.  scripts/trace_mlp.py decodes it.                                                     */

@@ -80,6 +80,7 @@ __constant__ MlpSide c_side[MAX_NETS];
 
 struct nfb_mlp {
   __nv_bfloat16* image;      // TOTAL_BLOCKS x 16 KB pre-swizzled weight blocks
+  __nv_bfloat16* image_t;    // transposed blocks for the data-gradient chain (68 x 16 KB)
   nfb::MlpSide* side;        // staging copy in global memory (written by the pack kernel)
   int cslot;                 // index into the __constant__ c_side table of this device
   int* abort_flag;           // set by the kernel if a barrier wait timed out
@@ -822,6 +823,8 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
 
 }  // namespace nfb
 
+#include "mlp_train.inl"
+
 // ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
@@ -849,7 +852,7 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
                      "mlp_create: fused kernel is built for D=8 W=256 input_ch=63 input_ch_views=27 skips=[4] "
                      "(got D=%d W=%d input_ch=%d input_ch_views=%d skip=%d)", D, W, input_ch, input_ch_views, skip);
   nfb_mlp* h = new nfb_mlp();
-  h->image = nullptr; h->side = nullptr; h->abort_flag = nullptr; h->cslot = -1;
+  h->image = nullptr; h->image_t = nullptr; h->side = nullptr; h->abort_flag = nullptr; h->cslot = -1;
   h->n_params = nfb::param_layout().total;
   cudaError_t e = cudaGetDevice(&h->device);
   if (e == cudaSuccess && (h->device < 0 || h->device >= 64)) { delete h; return nfb::fail(NFB_E_UNSUPPORTED, "mlp_create: device index out of range"); }
@@ -861,6 +864,7 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
     }
   }
   if (e == cudaSuccess) e = cudaMalloc(&h->image, (size_t)nfb::TOTAL_BLOCKS * nfb::CHUNK_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc(&h->image_t, (size_t)nfb::tr::TOTAL_BLOCKS_T * nfb::CHUNK_BYTES);
   if (e == cudaSuccess) e = cudaMalloc(&h->side, sizeof(nfb::MlpSide));
   if (e == cudaSuccess) e = cudaMalloc(&h->abort_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(h->abort_flag, 0, sizeof(int));
@@ -868,8 +872,12 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
     e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e != cudaSuccess) {
-    cudaFree(h->image); cudaFree(h->side); cudaFree(h->abort_flag);
+    cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag);
     release_cslot(h->device, h->cslot);
     delete h;
     return nfb::fail(NFB_E_CUDA, "mlp_create: %s", cudaGetErrorString(e));
@@ -886,6 +894,9 @@ int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* st
   nfb::pack_weights_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image, h->side);
   int rc = nfb::check_launch("mlp_update");
   if (rc) return rc;
+  nfb::tr::pack_weights_T_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image_t);
+  rc = nfb::check_launch("mlp_update.transposed");
+  if (rc) return rc;
   // stream-ordered device-to-device copy of the fp32 side parameters into this network's constant-memory entry
   NFB_CUDA(cudaMemcpyToSymbolAsync(nfb::c_side, h->side, sizeof(nfb::MlpSide), (size_t)h->cslot * sizeof(nfb::MlpSide),
                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -894,7 +905,7 @@ int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* st
 
 int nfb_mlp_destroy(nfb_mlp_t* h) {
   if (!h) return NFB_OK;
-  cudaFree(h->image); cudaFree(h->side); cudaFree(h->abort_flag);
+  cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag);
   release_cslot(h->device, h->cslot);
   delete h;
   return NFB_OK;
@@ -960,6 +971,53 @@ int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const floa
                       const float* rays, const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg,
                       void* stream) {
   return mlp_launch(h, mode, pts, dirs, rays, z_vals, R, S, raw, nsteps, dbg, stream);
+}
+
+// ---- training (bf16 tensor-core forward that saves activations, and the data-gradient chain) ----
+static int train_launch(int mode, const nfb_mlp_t* h, nfb::tr::TrainArgs& a, void* stream) {
+  const int64_t rows_per_unit = 2 * nfb::TILE_M * 2;
+  const int64_t nunits = (a.M + rows_per_unit - 1) / rows_per_unit;
+  int groups = nfb::sm_count() / 2;
+  if (nunits < groups) groups = (int)nunits;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(groups * 2));
+  cfg.blockDim = dim3(nfb::NUM_THREADS);
+  cfg.dynamicSmemBytes = nfb::SMEM_BYTES;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = (mode == nfb::tr::MODE_FWD)
+      ? cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD>, a)
+      : cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD>, a);
+  if (e != cudaSuccess) return nfb::fail(NFB_E_CUDA, "mlp_train: cluster launch: %s", cudaGetErrorString(e));
+  return nfb::check_launch(mode == nfb::tr::MODE_FWD ? "mlp_fwd_train" : "mlp_bwd_data");
+}
+
+// number of 128-row tiles the training images must hold for M = R*S samples (whole units of 512 rows)
+int64_t nfb_mlp_train_tiles(int64_t M) { return M <= 0 ? 0 : ((M + 511) / 512) * 4; }
+
+int nfb_mlp_fwd_train(const nfb_mlp_t* h, const float* rays, const float* z_vals, int R, int S, float* raw,
+                      void* act_img, uint32_t* mask, void* stream) {
+  NFB_REQUIRE(h && rays && z_vals && raw && act_img && mask, "mlp_fwd_train: null pointer");
+  NFB_REQUIRE(R >= 0 && S > 0, "mlp_fwd_train: R=%d S=%d", R, S);
+  if (R == 0) return NFB_OK;
+  nfb::tr::TrainArgs a{};
+  a.image = h->image; a.side = h->side; a.cslot = h->cslot; a.abort_flag = h->abort_flag;
+  a.rays = rays; a.z_vals = z_vals; a.M = (int64_t)R * S; a.S = S; a.raw = raw;
+  a.act_img = (char*)act_img; a.mask = mask;
+  return train_launch(nfb::tr::MODE_FWD, h, a, stream);
+}
+
+int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_t* mask, void* dy_img, void* stream) {
+  NFB_REQUIRE(h && g_raw && mask && dy_img, "mlp_bwd_data: null pointer");
+  NFB_REQUIRE(M >= 0, "mlp_bwd_data: M=%lld", (long long)M);
+  if (M == 0) return NFB_OK;
+  nfb::tr::TrainArgs a{};
+  a.image = h->image_t; a.side = h->side; a.cslot = h->cslot; a.abort_flag = h->abort_flag;
+  a.M = M; a.S = 1; a.g_raw = g_raw; a.mask = const_cast<uint32_t*>(mask); a.dy_img = (char*)dy_img;
+  return train_launch(nfb::tr::MODE_BWD, h, a, stream);
 }
 
 // Profiling aid: full forward with a timeline of CTA 0 written to trace [3][2048][4] uint64 (see FwdArgs::trace).

@@ -122,6 +122,19 @@ class NeRF(nn.Module):
                   self.rgb_linear.weight, self.rgb_linear.bias]
         return torch.cat([p.detach().reshape(-1).float() for p in parts])
 
+    def ordered_params(self):
+        """Parameters in the state_dict / nfb_mlp_update order."""
+        ps = []
+        for lin in self.pts_linears:
+            ps += [lin.weight, lin.bias]
+        ps += [self.views_linears[0].weight, self.views_linears[0].bias, self.feature_linear.weight, self.feature_linear.bias,
+               self.alpha_linear.weight, self.alpha_linear.bias, self.rgb_linear.weight, self.rgb_linear.bias]
+        return ps
+
+    def forward_rays_train(self, rays, z_vals):
+        """raw [R,S,4] with autograd through the bf16 tensor-core training kernels (rays [R,11], z_vals [R,S])."""
+        return ops.FusedMLPTrainFn.apply(self, rays, z_vals, *self.ordered_params())
+
     def _param_version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
@@ -140,6 +153,12 @@ class NeRF(nn.Module):
             self._fused.update(self.flat_params())
             self._fused_version = ver
         return self._fused
+
+
+def train_precision() -> str:
+    """'fp32' (default: layer-wise CUDA-core kernels, gradients within 1e-3 of the reference) or 'bf16'
+    (NERFAIL_B200_TRAIN=bf16: fused tensor-core forward/backward, mixed-precision gradients)."""
+    return os.environ.get("NERFAIL_B200_TRAIN", "fp32").lower()
 
 
 def mlp_precision() -> str:

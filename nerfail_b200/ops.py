@@ -506,3 +506,76 @@ def wgrad_bf16(dy_img: torch.Tensor, x_img: torch.Tensor, want_bias=True):
     if int(status.item()) != 0:
         raise RuntimeError("nfb_wgrad_bf16: pipeline barrier timed out")
     return dW, db
+
+
+def from_tile_image(img: torch.Tensor) -> torch.Tensor:
+    """Inverse of to_tile_image: [T, C, 128, 64] swizzled bf16 -> [T*128, C*64] float32 (test helper)."""
+    T, Cn = img.shape[0], img.shape[1]
+    t = img.reshape(T, Cn, 128, 8, 8)
+    r = torch.arange(128, device=img.device).reshape(1, 1, 128, 1, 1)
+    u = torch.arange(8, device=img.device).reshape(1, 1, 1, 8, 1)
+    un = torch.gather(t, 3, (u ^ (r & 7)).expand(T, Cn, 128, 8, 8))
+    return un.permute(0, 2, 1, 3, 4).reshape(T * 128, Cn * 64).float()
+
+
+class FusedMLPTrainFn(torch.autograd.Function):
+    """raw = NeRF(rays, z) on tensor cores with autograd: forward = nfb_mlp_fwd_train (saves bf16 activations as tile
+    images), backward = nfb_mlp_bwd_data (dY images) + one nfb_wgrad_bf16 product per weight matrix.
+    Gradients flow to the network parameters only (rays / depths are constants of the step, run_nerf.py:394)."""
+
+    @staticmethod
+    def forward(ctx, net, rays, z_vals, *params):
+        lib = _lib.load()
+        fused = net.fused()
+        rays, z_vals = _f32(rays), _f32(z_vals)
+        R, S = z_vals.shape
+        M = R * S
+        T = int(lib.nfb_mlp_train_tiles(M))
+        dev = rays.device
+        act = torch.empty((T, 40, 128, 64), dtype=torch.bfloat16, device=dev)
+        mask = torch.empty((T, 9, 128, 8), dtype=torch.int32, device=dev)
+        raw = torch.empty((R, S, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.nfb_mlp_fwd_train(fused._h, ptr(rays), ptr(z_vals), R, S, ptr(raw), ptr(act), ptr(mask), stream()),
+                  "nfb_mlp_fwd_train")
+        ctx.fused, ctx.M, ctx.T = fused, M, T
+        ctx.save_for_backward(act, mask)
+        return raw
+
+    @staticmethod
+    def backward(ctx, g_raw):
+        lib = _lib.load()
+        act, mask = ctx.saved_tensors
+        M, T = ctx.M, ctx.T
+        dev = act.device
+        g_raw = _f32(g_raw).reshape(M, 4)
+        dy = torch.empty((T, 38, 128, 64), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.nfb_mlp_bwd_data(ctx.fused._h, ptr(g_raw), M, ptr(mask), ptr(dy), stream()), "nfb_mlp_bwd_data")
+        h = lambda s_: act[:, 4 * s_: 4 * s_ + 4]                     # output of MMA step s_ (h_0..h_7, feature at 8)
+        dY = lambda l: dy[:, 6 + 4 * (7 - l): 10 + 4 * (7 - l)]       # dY of pts_linears.l
+        pe, dirs, hv = act[:, 38:39], act[:, 39:40], act[:, 36:38]
+        grads = []
+        for l in range(8):
+            if l == 0:
+                w, b = wgrad_bf16(dY(0), pe)
+                gw = w[:, :63].contiguous()
+            elif l == 5:
+                wh, b = wgrad_bf16(dY(5), h(4))
+                wp, _ = wgrad_bf16(dY(5), pe, want_bias=False)
+                gw = torch.cat([wp[:, :63], wh], 1)
+            else:
+                gw, b = wgrad_bf16(dY(l), h(l - 1))
+            grads += [gw, b]
+        wf, bv = wgrad_bf16(dy[:, 0:2], h(8))                         # views_linears.0: [feature, dirs]
+        wd, _ = wgrad_bf16(dy[:, 0:2], dirs, want_bias=False)
+        grads += [torch.cat([wf, wd[:, :27]], 1), bv]
+        gwf, gbf = wgrad_bf16(dy[:, 2:6], h(7))                       # feature_linear
+        grads += [gwf, gbf]
+        head = torch.zeros((T * 128, 128), dtype=torch.float32, device=dev)
+        head[:M, :4] = g_raw                                          # columns 0..2 = d/d rgb logits, 3 = d/d sigma
+        head_img = to_tile_image(head)
+        wa, bh = wgrad_bf16(head_img, h(7))                           # row 3 = alpha_linear.weight
+        wr, _ = wgrad_bf16(head_img, hv, want_bias=False)             # rows 0..2 = rgb_linear.weight
+        grads += [wa[3:4].contiguous(), bh[3:4].contiguous(), wr[:3].contiguous(), bh[:3].contiguous()]
+        return (None, None, None, *grads)

@@ -77,6 +77,11 @@ class NetworkQuery:
         """raw [R,S,4] for pts = o + d*z (run_nerf.py:381) without materialising pts when the fused path applies."""
         if ray_batch.shape[-1] == 11 and _fusable(network_fn, self.embed_fn, self.embeddirs_fn):
             return network_fn.fused().forward_rays(ray_batch, z_vals)
+        if (ray_batch.shape[-1] == 11 and torch.is_grad_enabled() and nerf.train_precision() == "bf16"
+                and isinstance(network_fn, NeRF) and network_fn.fused_supported()
+                and isinstance(self.embed_fn, nerf.Embedder) and self.embed_fn.multires == 10
+                and isinstance(self.embeddirs_fn, nerf.Embedder) and self.embeddirs_fn.multires == 4):
+            return network_fn.forward_rays_train(ray_batch, z_vals)
         rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
         viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]

@@ -184,3 +184,66 @@ def test_wgrad_bf16_tile_images(cuda, ntiles, ndy, nx):
     scale = float(ref_w.abs().max())
     assert float((dW.cpu().double() - ref_w).abs().max()) < 2e-5 * scale * max(1.0, ntiles ** 0.5) + 1e-4, "dW"
     assert float((db.cpu().double() - ref_b).abs().max()) < 1e-4 * float(ref_b.abs().max()) + 1e-3, "db"
+
+
+def _train_setup(cuda, R=37, S=64, seed=4):
+    import nerfail_b200 as nb
+    net = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
+    net.load_state_dict(synth.make_non_degenerate(synth.random_state_dict(seed), seed))
+    K, _ = synth.intrinsics(16, 16)
+    rays = no.camera_rays(16, 16, K, torch.tensor(synth.pose_spherical(70.0, -30.0, 4.0)[:3, :4]), 2.0, 6.0)[:R].contiguous()
+    z = no.coarse_depths(rays, S)
+    return net, rays.to(cuda), z.to(cuda)
+
+
+def test_fused_train_forward_saves_exact_activations(cuda):
+    """Training forward: raw identical to the inference kernel; saved tile images = bf16 of the per-step
+    activations the debug entry dumps; mask words = (activation > 0)."""
+    from nerfail_b200 import _lib, ops
+    net, rays, z = _train_setup(cuda)
+    R, S = z.shape
+    M = R * S
+    with torch.no_grad():
+        raw_inf = net.fused().forward_rays(rays, z)
+    raw = net.forward_rays_train(rays, z)
+    net.fused().status()
+    assert torch.equal(raw.detach(), raw_inf)
+    act, mask = raw.grad_fn.saved_tensors
+    flat = ops.from_tile_image(act)[:M]                      # [M, 40*64]
+    for s in (0, 3, 4, 7, 8):
+        _, dbg = net.fused().forward_rays(rays, z, nsteps=s + 1, want_dbg=True)
+        want = dbg.to(torch.bfloat16).float()
+        got = flat[:, s * 256:(s + 1) * 256]
+        assert torch.equal(got, want), f"saved activation of step {s}"
+        if s < 8:
+            words = mask[:, s].reshape(-1, 8)[:M].cpu().numpy().astype(np.uint32)
+            bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(M, 256).astype(bool)
+            assert np.array_equal(bits, (dbg > 0).cpu().numpy()), f"relu mask of step {s}"
+    # encoded point / direction chunks against the reference encoding (bf16 rounding of the kernel's own PE)
+    pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]).reshape(-1, 3).cpu()
+    pe_ref = no.positional_encoding(pts, 10)
+    got_pe = flat[:, 38 * 64: 38 * 64 + 63].cpu()
+    assert float((got_pe - pe_ref).abs().max()) < 1e-2
+
+
+def test_fused_train_backward_matches_fp32_autograd(cuda):
+    """bf16 tensor-core backward (data-gradient chain + wgrad GEMMs) against the fp32 layer-wise autograd path on the
+    same inputs and the same upstream gradient: mixed-precision tolerance (2 % relative L2 per tensor)."""
+    import nerfail_b200 as nb
+    net, rays, z = _train_setup(cuda, R=45, S=192, seed=5)
+    g = torch.Generator().manual_seed(1)
+    cot = torch.randn(rays.shape[0], z.shape[1], 4, generator=g).to(cuda)
+    raw = net.forward_rays_train(rays, z)
+    (raw * cot).sum().backward()
+    net.fused().status()
+    got = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad()
+    e10, _ = nb.get_embedder(10); e4, _ = nb.get_embedder(4)
+    pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]
+    raw32 = nb.run_network(pts, rays[:, 8:11].contiguous(), net, e10, e4)
+    (raw32 * cot).sum().backward()
+    assert float((raw.detach() - raw32.detach()).abs().mean()) < 2e-2 * float(raw32.abs().max())
+    for n, p in net.named_parameters():
+        ref = p.grad.double()
+        rel = float((got[n].double() - ref).norm() / (ref.norm() + 1e-30))
+        assert rel < 2e-2, (n, rel)
