@@ -226,9 +226,38 @@ def test_fused_train_forward_saves_exact_activations(cuda):
     assert float((got_pe - pe_ref).abs().max()) < 1e-2
 
 
+def _ste_bf16(t):
+    """bf16 rounding with a straight-through gradient (the kernels round activations/weights but differentiate through)."""
+    return t + (t.to(torch.bfloat16).float() - t).detach()
+
+
+def _mlp_bf16_ste(net, pts, dirs):
+    """Differentiable torch restatement of the fused kernel's numerics (same rounding points as
+    oracle.nerf_oracle.nerf_mlp_bf16_emulated): the 'ideal' gradient of the bf16 forward."""
+    F = torch.nn.functional
+    lin = lambda a, l: a @ _ste_bf16(l.weight).t() + l.bias
+    e_pts = _ste_bf16(no.positional_encoding(pts, 10))
+    e_dir = _ste_bf16(no.positional_encoding(dirs, 4))
+    h = e_pts
+    h32 = None
+    for i, l in enumerate(net.pts_linears):
+        h32 = F.relu(lin(h, l))
+        h = _ste_bf16(h32)
+        if i == 4:
+            h = torch.cat([e_pts, h], -1)
+    sigma = F.linear(h32, net.alpha_linear.weight, net.alpha_linear.bias)
+    feat = _ste_bf16(lin(h, net.feature_linear))
+    hv = F.relu(lin(torch.cat([feat, e_dir], -1), net.views_linears[0]))
+    rgb = F.linear(hv, net.rgb_linear.weight, net.rgb_linear.bias)
+    return torch.cat([rgb, sigma], -1)
+
+
 def test_fused_train_backward_matches_fp32_autograd(cuda):
-    """bf16 tensor-core backward (data-gradient chain + wgrad GEMMs) against the fp32 layer-wise autograd path on the
-    same inputs and the same upstream gradient: mixed-precision tolerance (2 % relative L2 per tensor)."""
+    """bf16 tensor-core backward (data-gradient chain + wgrad GEMMs), same inputs and upstream gradient, against
+    (a) torch autograd through a restatement of the kernel's own bf16 forward (straight-through rounding): what is
+        left is the bf16 rounding of the dY tiles / saved activations and relu-mask flips of near-zero units;
+    (b) the fp32 layer-wise autograd path: mixed-precision agreement (the fp32 forward has different activations
+        and relu masks) for these high-gain synthetic weights."""
     import nerfail_b200 as nb
     net, rays, z = _train_setup(cuda, R=45, S=192, seed=5)
     g = torch.Generator().manual_seed(1)
@@ -238,12 +267,23 @@ def test_fused_train_backward_matches_fp32_autograd(cuda):
     net.fused().status()
     got = {n: p.grad.clone() for n, p in net.named_parameters()}
     net.zero_grad()
-    e10, _ = nb.get_embedder(10); e4, _ = nb.get_embedder(4)
     pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]
+    dirs = rays[:, None, 8:11].expand(-1, z.shape[1], -1)
+    raw_e = _mlp_bf16_ste(net, pts.reshape(-1, 3), dirs.reshape(-1, 3)).reshape(raw.shape)
+    (raw_e * cot).sum().backward()
+    rel_e = {n: float((got[n].double() - p.grad.double()).norm() / (p.grad.double().norm() + 1e-30)) for n, p in net.named_parameters()}
+    print("vs bf16-forward autograd:", {k: round(v, 4) for k, v in rel_e.items()})
+    net.zero_grad()
+    e10, _ = nb.get_embedder(10); e4, _ = nb.get_embedder(4)
     raw32 = nb.run_network(pts, rays[:, 8:11].contiguous(), net, e10, e4)
     (raw32 * cot).sum().backward()
+    rel_32 = {n: float((got[n].double() - p.grad.double()).norm() / (p.grad.double().norm() + 1e-30)) for n, p in net.named_parameters()}
+    print("vs fp32 autograd:", {k: round(v, 4) for k, v in rel_32.items()})
     assert float((raw.detach() - raw32.detach()).abs().mean()) < 2e-2 * float(raw32.abs().max())
-    for n, p in net.named_parameters():
-        ref = p.grad.double()
-        rel = float((got[n].double() - ref).norm() / (ref.norm() + 1e-30))
-        assert rel < 2e-2, (n, rel)
+    # measured on B200: heads 0.1-0.4 %, view/feature layers 0.8 %, growing by ~0.8 % in quadrature per layer of bf16 dY
+    # rounding / mask flips to 2.5 % at pts_linears.0 (vs the bf16-forward ideal); 5-13 % vs the fp32 forward's gradient
+    for n, rel in rel_e.items():
+        lim = 6e-3 if ("alpha" in n or "rgb" in n) else 1.5e-2 if ("views" in n or "feature" in n) else 4e-2
+        assert rel < lim, (n, rel)
+    for n, rel in rel_32.items():
+        assert rel < (1e-2 if ("alpha" in n or "rgb" in n) else 0.2), (n, rel)
