@@ -101,13 +101,17 @@ NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, co
  * nfb_mlp_fwd_train = nfb_mlp_fwd (mode 1) that also leaves, per 128-row tile, every layer's bf16 activation as a tile
  * image act_img [tiles][40][16 KB] and the relu masks as bit words mask [tiles][9][128][8] (layout: csrc/mlp_train.inl).
  * nfb_mlp_bwd_data runs the data-gradient chain from g_raw [M,4] (d loss / d raw) and leaves every layer's dY as a tile
- * image dy_img [tiles][38][16 KB]; the weight gradients are then nfb_wgrad_bf16 products of the two images.
- * tiles = nfb_mlp_train_tiles(M).                                                                                   */
+ * image dy_img [tiles][39][16 KB] (chunk 38 = the upstream gradient itself, dY of the two heads).
+ * nfb_mlp_bwd_weights computes every weight / bias gradient of the network from the two images in ONE grouped launch
+ * (16 products dW = dY^T X, see nfb_wgrad_bf16) and ACCUMULATES them into grad [nfb_mlp_param_count] in state_dict
+ * order: zero grad once per step.  tiles = nfb_mlp_train_tiles(M).  A barrier time-out is reported by nfb_mlp_status. */
 NFB_API int64_t nfb_mlp_train_tiles(int64_t M);
 NFB_API int nfb_mlp_fwd_train(const nfb_mlp_t* h, const float* rays, const float* z_vals, int R, int S, float* raw,
                               void* act_img, uint32_t* mask, void* stream);
 NFB_API int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_t* mask, void* dy_img,
                              void* stream);
+NFB_API int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_img, int64_t ntiles, float* grad,
+                                void* stream);
 
 /* Profiling aid: the full forward (mode 1) while CTA 0 records a timeline of its barrier waits into
  * trace [3 roles][2048 events][4] uint64 = (tag, clock begin, clock end, aux); roles: 0 weight producer, 1 MMA warp,
@@ -141,14 +145,12 @@ NFB_API int64_t nfb_linear_bwd_weight_workspace(int64_t M, int N, int K);
  * replaces: the wgrad GEMMs of loss.backward() (run_nerf.py:791) for one layer:
  *   dW[n, k] = sum_rows dY[row, n] * X[row, k],   db[n] = sum_rows dY[row, n]
  * dy: ndy in {2,4} chunks per tile (n = 64*ndy), x: nx in {1,2,4} chunks (k = 64*nx); *_tile_pitch = bytes between tiles.
- * Each of nfb_wgrad_parts() CTAs writes a partial: part_w [parts][64*ndy][64*nx], part_b [parts][64*ndy] (or NULL);
- * nfb_wgrad_reduce sums partials in a fixed order into out[r*ld + col0 + c] for c < cols_valid.  status: device int
- * that the kernel raises if a pipeline barrier timed out.                                                          */
-NFB_API int nfb_wgrad_parts(void);
+ * The per-CTA partial sums are ACCUMULATED with L2 float reductions into out_w[(n - row_begin)*ld + col0 + k] for
+ * n in [row_begin, row_end), k < cols_valid, and into out_b[n - row_begin] (or NULL): zero the gradients once per step.
+ * status: device int that the kernel raises if a pipeline barrier timed out.                                        */
 NFB_API int nfb_wgrad_bf16(const void* dy, int64_t dy_tile_pitch, int ndy, const void* x, int64_t x_tile_pitch, int nx,
-                           int64_t ntiles, float* part_w, float* part_b, int* status, void* stream);
-NFB_API int nfb_wgrad_reduce(const float* part, int nparts, int rows, int cols, int cols_valid, float* out, int ld, int col0,
-                             int accumulate, void* stream);
+                           int64_t ntiles, float* out_w, int ld, int col0, int cols_valid, int row_begin, int row_end,
+                           float* out_b, int* status, void* stream);
 
 /* Alpha compositing. replaces: run_nerf.py:262-305 (raw2outputs) and, when pts_max != NULL,
  * nerf_to_coord.py:418-421 (arg-max-weight point o + d*z[argmax], first maximum wins).

@@ -36,6 +36,21 @@ inline int check_launch(const char* what) {
 
 int sm_count();   // cached multiprocessor count of the current device (148 on B200)
 
+// One product dW = dY^T X of a grouped tensor-core weight-gradient launch (wgrad.cu).  dy / x point at chunk 0 of tile 0
+// of a bf16 tile image; *_pitch = bytes between tiles; ndy / nx = 64-column chunks (dY: 2 or 4, X: 1, 2 or 4); dY chunks
+// [ndy_real, ndy) are taken from a block of zeros.  Output window: rows [row_begin, row_end) x cols_valid columns are
+// ACCUMULATED into out_w[(row - row_begin) * ld + col0 + c], the column sums of dY into out_b[row - row_begin] (or null).
+struct WgradJob {
+  const void* dy;  int64_t dy_pitch;
+  const void* x;   int64_t x_pitch;
+  float* out_w;
+  float* out_b;
+  int ndy, ndy_real, nx;
+  int ld, col0, cols_valid, row_begin, row_end;
+};
+int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const void* zero16k, int* status, void* stream,
+                         const char* what);
+
 // ---- device ------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 

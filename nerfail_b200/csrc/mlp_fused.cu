@@ -84,6 +84,7 @@ struct nfb_mlp {
   nfb::MlpSide* side;        // staging copy in global memory (written by the pack kernel)
   int cslot;                 // index into the __constant__ c_side table of this device
   int* abort_flag;           // set by the kernel if a barrier wait timed out
+  void* zero16k;             // 16 KB of zeros: the padding dY chunk of the head weight-gradient products
   int device;
   int64_t n_params;
 };
@@ -852,7 +853,7 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
                      "mlp_create: fused kernel is built for D=8 W=256 input_ch=63 input_ch_views=27 skips=[4] "
                      "(got D=%d W=%d input_ch=%d input_ch_views=%d skip=%d)", D, W, input_ch, input_ch_views, skip);
   nfb_mlp* h = new nfb_mlp();
-  h->image = nullptr; h->image_t = nullptr; h->side = nullptr; h->abort_flag = nullptr; h->cslot = -1;
+  h->image = nullptr; h->image_t = nullptr; h->side = nullptr; h->abort_flag = nullptr; h->zero16k = nullptr; h->cslot = -1;
   h->n_params = nfb::param_layout().total;
   cudaError_t e = cudaGetDevice(&h->device);
   if (e == cudaSuccess && (h->device < 0 || h->device >= 64)) { delete h; return nfb::fail(NFB_E_UNSUPPORTED, "mlp_create: device index out of range"); }
@@ -868,6 +869,8 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
   if (e == cudaSuccess) e = cudaMalloc(&h->side, sizeof(nfb::MlpSide));
   if (e == cudaSuccess) e = cudaMalloc(&h->abort_flag, sizeof(int));
   if (e == cudaSuccess) e = cudaMemset(h->abort_flag, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->zero16k, nfb::CHUNK_BYTES);
+  if (e == cudaSuccess) e = cudaMemset(h->zero16k, 0, nfb::CHUNK_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e == cudaSuccess)
@@ -877,7 +880,7 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e != cudaSuccess) {
-    cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag);
+    cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag); cudaFree(h->zero16k);
     release_cslot(h->device, h->cslot);
     delete h;
     return nfb::fail(NFB_E_CUDA, "mlp_create: %s", cudaGetErrorString(e));
@@ -905,7 +908,7 @@ int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* st
 
 int nfb_mlp_destroy(nfb_mlp_t* h) {
   if (!h) return NFB_OK;
-  cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag);
+  cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag); cudaFree(h->zero16k);
   release_cslot(h->device, h->cslot);
   delete h;
   return NFB_OK;
@@ -1018,6 +1021,35 @@ int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, const ui
   a.image = h->image_t; a.side = h->side; a.cslot = h->cslot; a.abort_flag = h->abort_flag;
   a.M = M; a.S = 1; a.g_raw = g_raw; a.mask = const_cast<uint32_t*>(mask); a.dy_img = (char*)dy_img;
   return train_launch(nfb::tr::MODE_BWD, h, a, stream);
+}
+
+// Weight gradients of one network from the saved images: 16 products dW = dY^T X (+ bias sums) in ONE grouped tensor-core
+// launch, accumulated into grad [n_params] in state_dict order (the caller zeroes it once per step).
+int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_img, int64_t ntiles, float* grad, void* stream) {
+  NFB_REQUIRE(h && act_img && dy_img && grad, "mlp_bwd_weights: null pointer");
+  NFB_REQUIRE(ntiles >= 0, "mlp_bwd_weights: ntiles=%lld", (long long)ntiles);
+  if (ntiles == 0) return NFB_OK;
+  using namespace nfb;
+  const ParamLayout pl = param_layout();
+  const int64_t ap = (int64_t)tr::FWD_CHUNKS * CHUNK_BYTES, dp = (int64_t)tr::BWD_CHUNKS * CHUNK_BYTES;
+  auto A = [&](int chunk) { return (const void*)((const char*)act_img + (int64_t)chunk * CHUNK_BYTES); };
+  auto D = [&](int chunk) { return (const void*)((const char*)dy_img + (int64_t)chunk * CHUNK_BYTES); };
+  auto dYl = [&](int l) { return D(6 + 4 * (7 - l)); };
+  WgradJob jobs[16];
+  int n = 0;
+  // pts_linears.l, heaviest first so the equal-cost cut starts on full-width products
+  for (int l = 1; l < 8; ++l) {
+    const int ld = (l == 5) ? W_ + CH_PTS : W_;
+    jobs[n++] = WgradJob{dYl(l), dp, A(4 * (l - 1)), ap, grad + pl.w_pts[l], grad + pl.b_pts[l], 4, 4, 4, ld, l == 5 ? CH_PTS : 0, W_, 0, W_};
+  }
+  jobs[n++] = WgradJob{D(2), dp, A(28), ap, grad + pl.w_feat, grad + pl.b_feat, 4, 4, 4, W_, 0, W_, 0, W_};                       // feature_linear
+  jobs[n++] = WgradJob{D(0), dp, A(tr::IMG_FEAT), ap, grad + pl.w_views, grad + pl.b_views, 2, 2, 4, W_ + CH_DIR, 0, W_, 0, 128};    // views_linears.0 [:, :256]
+  jobs[n++] = WgradJob{D(tr::IMG_DY_HEAD), dp, A(28), ap, grad + pl.w_alpha, grad + pl.b_alpha, 2, 1, 4, W_, 0, W_, 3, 4};           // alpha_linear (head row 3)
+  jobs[n++] = WgradJob{D(tr::IMG_DY_HEAD), dp, A(tr::IMG_HV), ap, grad + pl.w_rgb, grad + pl.b_rgb, 2, 1, 2, 128, 0, 128, 0, 3};     // rgb_linear (head rows 0..2)
+  jobs[n++] = WgradJob{dYl(0), dp, A(tr::IMG_PE), ap, grad + pl.w_pts[0], grad + pl.b_pts[0], 4, 4, 1, CH_PTS, 0, CH_PTS, 0, W_};    // pts_linears.0
+  jobs[n++] = WgradJob{dYl(5), dp, A(tr::IMG_PE), ap, grad + pl.w_pts[5], nullptr, 4, 4, 1, W_ + CH_PTS, 0, CH_PTS, 0, W_};          // pts_linears.5 [:, :63] (skip input)
+  jobs[n++] = WgradJob{D(0), dp, A(tr::IMG_DIR), ap, grad + pl.w_views, nullptr, 2, 2, 1, W_ + CH_DIR, W_, CH_DIR, 0, 128};          // views_linears.0 [:, 256:]
+  return launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, stream, "mlp_bwd_weights");
 }
 
 // Profiling aid: full forward with a timeline of CTA 0 written to trace [3][2048][4] uint64 (see FwdArgs::trace).

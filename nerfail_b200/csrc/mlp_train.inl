@@ -12,14 +12,16 @@
 // Tile-image chunk indices (16 KB chunks, 128 rows x 64 columns, 128-byte swizzle):
 //   forward  : h_s (s = 0..7) at 4 s .. 4 s + 3, feature at 32..35, view-layer output at 36..37, encoded point 38,
 //              encoded direction 39                                            -> FWD_CHUNKS = 40 per tile
-//   backward : dY_views 0..1, dY_feature 2..5, dY_l (l = 7..0) at 6 + 4 (7 - l)  -> BWD_CHUNKS = 38 per tile
+//   backward : dY_views 0..1, dY_feature 2..5, dY_l (l = 7..0) at 6 + 4 (7 - l), head chunk 38 (columns 0..3 = the upstream
+//              gradient of the rgb logits and of sigma, the rest zero: dY of the two heads) -> BWD_CHUNKS = 39 per tile
 //   masks    : [tile][9][128 rows][8 words]: words of h_0..h_7 (index 0..7) and of the view layer (index 8, 4 words)
 
 namespace nfb {
 namespace tr {
 
 constexpr int MODE_FWD = 1, MODE_BWD = 2;
-constexpr int FWD_CHUNKS = 40, BWD_CHUNKS = 38;
+constexpr int FWD_CHUNKS = 40, BWD_CHUNKS = 39;
+constexpr int IMG_DY_HEAD = 38;
 constexpr int IMG_FEAT = 32, IMG_HV = 36, IMG_PE = 38, IMG_DIR = 39;
 constexpr int MASK_WORDS_PER_TILE = 9 * 128 * 8;
 constexpr int BWD_STEPS = 9;
@@ -40,7 +42,7 @@ struct TrainArgs {
   const float* g_raw;             // [M,4] in         (MODE_BWD)
   char* act_img;                  // [ntiles][40][16 KB]  written by MODE_FWD
   uint32_t* mask;                 // [ntiles][9][128][8]  written by MODE_FWD, read by MODE_BWD
-  char* dy_img;                   // [ntiles][38][16 KB]  written by MODE_BWD
+  char* dy_img;                   // [ntiles][39][16 KB]  written by MODE_BWD
 };
 
 // transposed weight image for the data-gradient chain
@@ -295,9 +297,21 @@ mlp_train_kernel(const TrainArgs a) {
           const uint32_t addr = cb + row * 128 + (((u ^ (row & 7)) & 7) << 4);
           st_shared_v4(addr, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
+        // head chunk (dY of rgb_linear / alpha_linear for the weight-gradient GEMMs): row = [g_rgb, g_sigma, 0 ...]
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = hcol * 4 + u;
+          const uint32_t addr = pe + row * 128 + (((unit ^ (row & 7)) & 7) << 4);
+          if (unit == 0) st_shared_v4(addr, pack_bf16(gr.x, gr.y), pack_bf16(gr.z, gr.w), 0u, 0u);
+          else st_shared_v4(addr, 0u, 0u, 0u, 0u);
+        }
         fence_proxy_async();
         slot_sync();
-        if (tslot == 0) { bulk_s2g(dy_tile, act, 2 * CHUNK_BYTES); bulk_commit(); }
+        if (tslot == 0) {
+          bulk_s2g(dy_tile, act, 2 * CHUNK_BYTES);
+          bulk_s2g(dy_tile + (int64_t)IMG_DY_HEAD * CHUNK_BYTES, pe, CHUNK_BYTES);
+          bulk_commit();
+        }
       }
       signal_a_ready();
 

@@ -11,7 +11,9 @@
 //   MMA      = M 128 (two dY chunks) x N 64*nx x K 16 rows, fp32 accumulators for both M halves stay in TMEM (<= 512
 //              columns) across all tiles of the CTA
 //   bias     = 4 CUDA-core warps sum the dY slices of each stage out of shared memory
-//   epilogue = per-CTA partial [256, N] (+ [256]) to a workspace; nfb_wgrad_reduce sums partials in fixed order.
+//   epilogue = a CTA adds its partial [256, N] (+ [256]) into the gradient tensor with coalesced red.global.add.f32
+//   grouped  = one launch computes every product of a network: a job table, (job, tile) pairs cut into equal-cost
+//              contiguous ranges, one range per CTA (see job_segment)
 // HBM-bound by design: 1 KB per row and layer against 2*256*256 FLOP.
 #include "common.cuh"
 
@@ -24,7 +26,8 @@ constexpr int MAX_CHUNKS = 8;                           // 4 dY + 4 X
 constexpr int STAGE_BYTES = MAX_CHUNKS * SLICE_BYTES;   // 64 KB
 constexpr int NSTAGE = 3;
 constexpr int SM_BAR = NSTAGE * STAGE_BYTES;
-constexpr int SMEM_BYTES = SM_BAR + 256;
+constexpr int SM_SCRATCH = SM_BAR + 256;                  // 4 epilogue warps x [32][33] floats (transpose for coalesced reductions)
+constexpr int SMEM_BYTES = SM_SCRATCH + 4 * 32 * 33 * 4;
 constexpr int THREADS = 32 * 10;                        // warp 0 producer, 1 MMA/TMEM, 2-5 epilogue, 6-9 bias sums
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,34 +87,67 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
+constexpr int MAX_JOBS = 16;
+
+// One product dW = dY^T X of a grouped launch.  dY chunks [ndy_real, ndy) are read from a 16 KB block of zeros (pitch 0,
+// L2 resident) so that a product with fewer than 128 output rows still fills an M = 128 MMA.
+struct Job {
+  const char* dy;  int64_t dy_pitch;    // chunk 0 of tile 0; bytes between tiles
+  const char* x;   int64_t x_pitch;
+  float* out_w;                         // accumulated into out_w[(row - row_begin) * ld + col0 + c], c < cols_valid
+  float* out_b;                         // accumulated into out_b[row - row_begin] (column sums of dY), or null
+  int ndy, ndy_real, nx;                // 64-column chunks: dY (2 or 4), of which read from HBM, X (1, 2 or 4)
+  int ld, col0, cols_valid, row_begin, row_end;
+};
+
 struct Args {
-  const char* dy;  int64_t dy_tile_pitch;  int ndy;     // bytes between tiles; number of 64-column chunks (2 or 4)
-  const char* x;   int64_t x_tile_pitch;   int nx;      // 1, 2 or 4 chunks (N = 64*nx)
+  Job job[MAX_JOBS];
+  int njobs;
   int64_t ntiles;
-  float* part_w;     // [grid][64*ndy][64*nx]
-  float* part_b;     // [grid][64*ndy] or null
+  const char* zero;                     // 16 KB of zeros (only read when some job has ndy_real < ndy)
   int* flag;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const Args a) {
+// Work split: the (job, tile) pairs, jobs in table order, are cut into gridDim.x contiguous ranges of equal HBM cost
+// (cost of a tile of job j = ndy_real + nx chunks).  A CTA therefore works on one to three consecutive jobs, keeps a
+// job's whole dW in TMEM while it walks that job's tiles and flushes it once per job.
+struct Segment { int64_t lo, hi; };
+__device__ __forceinline__ Segment job_segment(const Args& a, int j, int64_t cost_before, int64_t cost_total) {
+  const int64_t W = a.ntiles * cost_total;
+  const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
+  const int64_t base = cost_before * a.ntiles;
+  const int64_t c = a.job[j].ndy_real + a.job[j].nx;
+  auto cut = [&](int64_t w) -> int64_t {
+    if (w <= base) return 0;
+    const int64_t t = (w - base + c - 1) / c;
+    return t < a.ntiles ? t : a.ntiles;
+  };
+  return Segment{cut(w0), cut(w1)};
+}
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   const uint32_t bar0 = base + SM_BAR;
   auto FULL_B = [&](int s) { return bar0 + 8 * s; };
   auto EMPTY_B = [&](int s) { return bar0 + 8 * (NSTAGE + s); };
   const uint32_t DONE_B = bar0 + 8 * (2 * NSTAGE);
-  const uint32_t tmem_slot = bar0 + 8 * (2 * NSTAGE + 1);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGE + 1));
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t FREE_B = bar0 + 8 * (2 * NSTAGE + 1);
+  const uint32_t tmem_slot = bar0 + 8 * (2 * NSTAGE + 2);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGE + 2));
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   volatile int* flag = a.flag;
-  const int nchunks = a.ndy + a.nx;
-  const int N = 64 * a.nx;
-  const int mhalves = a.ndy / 2;
 
   if (threadIdx.x == 0) {
     if (base & 1023u) *flag = 1;
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL_B(s), 1); mbar_init(EMPTY_B(s), 1 + (a.part_b ? a.ndy : 0)); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(FULL_B(s), 1); mbar_init(EMPTY_B(s), 1 + 4); }
     mbar_init(DONE_B, 1);
+    mbar_init(FREE_B, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -123,165 +159,214 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const Args a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // this CTA's tiles: blockIdx, blockIdx + grid, ...; each tile = 2 stages of 64 rows
-  const int64_t my_tiles = a.ntiles > blockIdx.x ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t nstages_total = my_tiles * 2;
+  int64_t cost_total = 0;
+  for (int j = 0; j < a.njobs; ++j) cost_total += a.job[j].ndy_real + a.job[j].nx;
 
   if (warp == 0) {
-    for (int64_t it = 0; it < nstages_total; ++it) {
-      const int st = (int)(it % NSTAGE);
-      const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
-      mbar_wait(EMPTY_B(st), ph ^ 1, flag);
-      if (elect_one()) {
-        const int64_t tile = blockIdx.x + (it >> 1) * gridDim.x;
-        const int half = (int)(it & 1);
-        mbar_arrive_expect_tx(FULL_B(st), nchunks * SLICE_BYTES);
-        const uint32_t dst = base + st * STAGE_BYTES;
-        for (int c = 0; c < a.ndy; ++c)
-          bulk_g2s(dst + c * SLICE_BYTES, a.dy + tile * a.dy_tile_pitch + (int64_t)c * 16384 + half * SLICE_BYTES, SLICE_BYTES, FULL_B(st));
-        for (int c = 0; c < a.nx; ++c)
-          bulk_g2s(dst + (a.ndy + c) * SLICE_BYTES, a.x + tile * a.x_tile_pitch + (int64_t)c * 16384 + half * SLICE_BYTES, SLICE_BYTES, FULL_B(st));
+    // ================= producer: 64-row slices of every chunk of a tile, one stage per half tile =================
+    int64_t it = 0, cost_before = 0;
+    for (int j = 0; j < a.njobs; ++j) {
+      const Job& jb = a.job[j];
+      const Segment sg = job_segment(a, j, cost_before, cost_total);
+      cost_before += jb.ndy_real + jb.nx;
+      for (int64_t tile = sg.lo; tile < sg.hi; ++tile) {
+        for (int half = 0; half < 2; ++half, ++it) {
+          const int st = (int)(it % NSTAGE);
+          const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+          mbar_wait(EMPTY_B(st), ph ^ 1, flag);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(FULL_B(st), (jb.ndy + jb.nx) * SLICE_BYTES);
+            const uint32_t dst = base + st * STAGE_BYTES;
+            for (int c = 0; c < jb.ndy; ++c) {
+              const char* src = c < jb.ndy_real ? jb.dy + tile * jb.dy_pitch + (int64_t)c * 16384 + half * SLICE_BYTES : a.zero;
+              bulk_g2s(dst + c * SLICE_BYTES, src, SLICE_BYTES, FULL_B(st));
+            }
+            for (int c = 0; c < jb.nx; ++c)
+              bulk_g2s(dst + (jb.ndy + c) * SLICE_BYTES, jb.x + tile * jb.x_pitch + (int64_t)c * 16384 + half * SLICE_BYTES,
+                       SLICE_BYTES, FULL_B(st));
+          }
+        }
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = idesc_mn(N);
-    for (int64_t it = 0; it < nstages_total; ++it) {
-      const int st = (int)(it % NSTAGE);
-      const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
-      mbar_wait(FULL_B(st), ph, flag);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sbase = base + st * STAGE_BYTES;
-      if (elect_one()) {
-        for (int mh = 0; mh < mhalves; ++mh) {
-#pragma unroll
-          for (int k = 0; k < ROWS_PER_STAGE / 16; ++k) {
-            const uint64_t ad = desc_mn(sbase + (2 * mh) * SLICE_BYTES + k * 2048, SLICE_BYTES);
-            const uint64_t bd = desc_mn(sbase + a.ndy * SLICE_BYTES + k * 2048, SLICE_BYTES);
-            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                :: "r"(tmem_base + mh * 256), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
-          }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(EMPTY_B(st)) : "memory");
-        if (it == nstages_total - 1)
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(DONE_B) : "memory");
+    // ================= MMA issuer: dW (both 128-row halves) accumulates in TMEM over the job's tiles =================
+    int64_t it = 0, cost_before = 0;
+    uint32_t seg = 0;
+    for (int j = 0; j < a.njobs; ++j) {
+      const Job& jb = a.job[j];
+      const Segment sg = job_segment(a, j, cost_before, cost_total);
+      cost_before += jb.ndy_real + jb.nx;
+      if (sg.hi <= sg.lo) continue;
+      const uint32_t idesc = idesc_mn(64 * jb.nx);
+      const int mhalves = jb.ndy / 2;
+      if (seg > 0) {                                   // the previous job's accumulators must have been drained
+        mbar_wait(FREE_B, (seg - 1) & 1, flag);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-    }
-  } else if (warp >= 6) {
-    // ---- bias sums: warp (6 + c) owns dY chunk c; lane = (row group of 4) x (16-byte unit = 8 columns) ----
-    const int c = warp - 6;
-    if (a.part_b && c < a.ndy) {
-      float acc8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc8[j] = 0.f;
-      const int unit = lane & 7, rg = lane >> 3;
-      for (int64_t it = 0; it < nstages_total; ++it) {
+      const int64_t nst = (sg.hi - sg.lo) * 2;
+      for (int64_t i = 0; i < nst; ++i, ++it) {
         const int st = (int)(it % NSTAGE);
         const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
         mbar_wait(FULL_B(st), ph, flag);
-        const uint8_t* sl = smem + st * STAGE_BYTES + c * SLICE_BYTES;
-        for (int r = rg; r < ROWS_PER_STAGE; r += 4) {
-          const uint4 v = *reinterpret_cast<const uint4*>(sl + r * 128 + (((unit ^ (r & 7)) & 7) << 4));
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sbase = base + st * STAGE_BYTES;
+        if (elect_one()) {
+          for (int mh = 0; mh < mhalves; ++mh) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            acc8[2 * j] += __uint_as_float(w[j] << 16);
-            acc8[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+            for (int k = 0; k < ROWS_PER_STAGE / 16; ++k) {
+              const uint64_t ad = desc_mn(sbase + (2 * mh) * SLICE_BYTES + k * 2048, SLICE_BYTES);
+              const uint64_t bd = desc_mn(sbase + jb.ndy * SLICE_BYTES + k * 2048, SLICE_BYTES);
+              const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                  :: "r"(tmem_base + mh * 256), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(EMPTY_B(st)) : "memory");
+          if (i == nst - 1)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(DONE_B) : "memory");
+        }
+      }
+      ++seg;
+    }
+  } else if (warp >= 6) {
+    // ================= bias sums: warp (6 + c) owns dY chunk c; lane = (row group of 4) x (16-byte unit = 8 columns) ====
+    const int c = warp - 6;
+    const int unit = lane & 7, rg = lane >> 3;
+    int64_t it = 0, cost_before = 0;
+    for (int j = 0; j < a.njobs; ++j) {
+      const Job& jb = a.job[j];
+      const Segment sg = job_segment(a, j, cost_before, cost_total);
+      cost_before += jb.ndy_real + jb.nx;
+      if (sg.hi <= sg.lo) continue;
+      const bool mine = jb.out_b && c < jb.ndy_real;
+      float acc8[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc8[q] = 0.f;
+      const int64_t nst = (sg.hi - sg.lo) * 2;
+      for (int64_t i = 0; i < nst; ++i, ++it) {
+        const int st = (int)(it % NSTAGE);
+        const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+        mbar_wait(FULL_B(st), ph, flag);
+        if (mine) {
+          const uint8_t* sl = smem + st * STAGE_BYTES + c * SLICE_BYTES;
+          for (int r = rg; r < ROWS_PER_STAGE; r += 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sl + r * 128 + (((unit ^ (r & 7)) & 7) << 4));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc8[2 * q] += __uint_as_float(w[q] << 16);
+              acc8[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+            }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(EMPTY_B(st));
       }
+      if (mine) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 8);
-        acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 16);
-      }
-      if (rg == 0) {
+        for (int q = 0; q < 8; ++q) {
+          acc8[q] += __shfl_xor_sync(0xffffffffu, acc8[q], 8);
+          acc8[q] += __shfl_xor_sync(0xffffffffu, acc8[q], 16);
+        }
+        if (rg == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a.part_b[(int64_t)blockIdx.x * 64 * a.ndy + c * 64 + unit * 8 + j] = acc8[j];
+          for (int q = 0; q < 8; ++q) {
+            const int r = c * 64 + unit * 8 + q;
+            if (r >= jb.row_begin && r < jb.row_end) red_add_f32(jb.out_b + (r - jb.row_begin), acc8[q]);
+          }
+        }
       }
     }
   } else {
-    // ---- final epilogue: TMEM -> per-CTA partial ----
-    if (nstages_total > 0) {
-      mbar_wait(DONE_B, 0, flag);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
+    // ================= epilogue: TMEM -> shared-memory transpose -> coalesced L2 reductions into the gradient =========
     const int q = warp & 3;
-    for (int mh = 0; mh < mhalves; ++mh) {
-      const int row = mh * 128 + q * 32 + lane;
-      float* out = a.part_w + ((int64_t)blockIdx.x * 64 * a.ndy + row) * N;
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        if (nstages_total > 0) {
+    float* scr = reinterpret_cast<float*>(smem + SM_SCRATCH) + (warp - 2) * (32 * 33);
+    int64_t cost_before = 0;
+    uint32_t seg = 0;
+    for (int j = 0; j < a.njobs; ++j) {
+      const Job& jb = a.job[j];
+      const Segment sg = job_segment(a, j, cost_before, cost_total);
+      cost_before += jb.ndy_real + jb.nx;
+      if (sg.hi <= sg.lo) continue;
+      mbar_wait(DONE_B, seg & 1, flag);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int N = 64 * jb.nx, mhalves = jb.ndy / 2;
+      for (int mh = 0; mh < mhalves; ++mh) {
+        const int row0 = mh * 128 + q * 32;                      // this warp's 32 output rows (TMEM lanes q*32 ..)
+        if (row0 >= jb.row_end || row0 + 32 <= jb.row_begin) continue;
+        for (int c0 = 0; c0 < N && c0 < jb.cols_valid; c0 += 32) {
+          uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q << 5) << 16) + mh * 256 + c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
+          for (int t = 0; t < 32; ++t) scr[lane * 33 + t] = __uint_as_float(v[t]);
+          __syncwarp();
+          const bool col_ok = c0 + lane < jb.cols_valid;
+          for (int r = 0; r < 32; ++r) {
+            const int row = row0 + r;
+            if (row >= jb.row_begin && row < jb.row_end && col_ok)
+              red_add_f32(jb.out_w + (int64_t)(row - jb.row_begin) * jb.ld + jb.col0 + c0 + lane, scr[r * 33 + lane]);
+          }
+          __syncwarp();
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<float4*>(out + c0)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(FREE_B);
+      ++seg;
     }
-    if (a.part_b && nstages_total == 0 && warp == 2)
-      for (int j = lane; j < 64 * a.ndy; j += 32) a.part_b[(int64_t)blockIdx.x * 64 * a.ndy + j] = 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512) : "memory");
 }
 
-// out[r * ld + col0 + c] (+)= sum_p part[p][r][c]  for r < rows, c < cols_valid (cols = pitch of the partial)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nparts, int rows, int cols, int cols_valid,
-                                    float* __restrict__ out, int ld, int col0, int accumulate) {
-  const int64_t n = (int64_t)rows * cols_valid;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(e / cols_valid), c = (int)(e % cols_valid);
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[((int64_t)p * rows + r) * cols + c];
-    float* dst = out + (int64_t)r * ld + col0 + c;
-    *dst = accumulate ? *dst + s : s;
+}  // namespace wg
+
+// Launches the grouped weight-gradient kernel (declared in common.cuh; the NeRF job table is built in mlp_fused.cu).
+int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const void* zero16k, int* status, void* stream,
+                         const char* what) {
+  NFB_REQUIRE(jobs && njobs > 0 && njobs <= wg::MAX_JOBS && status, "%s: bad job table", what);
+  if (ntiles <= 0) return NFB_OK;
+  wg::Args a{};
+  int64_t cost = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const WgradJob& s = jobs[j];
+    NFB_REQUIRE(s.dy && s.x && s.out_w, "%s: job %d: null pointer", what, j);
+    NFB_REQUIRE((s.ndy == 2 || s.ndy == 4) && s.ndy_real >= 1 && s.ndy_real <= s.ndy && (s.nx == 1 || s.nx == 2 || s.nx == 4),
+                "%s: job %d: ndy=%d (%d real) nx=%d", what, j, s.ndy, s.ndy_real, s.nx);
+    NFB_REQUIRE(s.ndy_real == s.ndy || zero16k, "%s: job %d needs the zero block", what, j);
+    NFB_REQUIRE(s.dy_pitch % 16 == 0 && s.x_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(s.dy) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(s.x) & 15) == 0, "%s: job %d: images must be 16-byte aligned", what, j);
+    NFB_REQUIRE(s.cols_valid > 0 && s.cols_valid <= 64 * s.nx && s.row_begin >= 0 && s.row_end <= 64 * s.ndy &&
+                s.row_begin < s.row_end && s.ld >= s.col0 + s.cols_valid, "%s: job %d: bad output window", what, j);
+    a.job[j] = wg::Job{(const char*)s.dy, s.dy_pitch, (const char*)s.x, s.x_pitch, s.out_w, s.out_b,
+                       s.ndy, s.ndy_real, s.nx, s.ld, s.col0, s.cols_valid, s.row_begin, s.row_end};
+    cost += s.ndy_real + s.nx;
   }
+  a.njobs = njobs; a.ntiles = ntiles; a.zero = (const char*)zero16k; a.flag = status;
+  NFB_CUDA(cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
+  int64_t grid = sm_count();
+  if ((int64_t)njobs * ntiles < grid) grid = (int64_t)njobs * ntiles;
+  wg::wgrad_kernel<<<(unsigned)grid, wg::THREADS, wg::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  return check_launch(what);
 }
 
-}  // namespace wg
 }  // namespace nfb
 
 extern "C" {
 
-// Number of CTAs nfb_wgrad_bf16 launches (= leading dimension of the partial buffers).
-int nfb_wgrad_parts(void) { return nfb::sm_count(); }
-
 // dy / x: tile images (see header of this file); ndy in {2,4}, nx in {1,2,4}.
-// part_w: [parts][64*ndy][64*nx] fp32, part_b: [parts][64*ndy] fp32 or NULL, status: device int (0 = ok).
+// Accumulates (L2 float reductions) dW rows [row_begin, row_end) x columns [0, cols_valid) into
+// out_w[(row - row_begin) * ld + col0 + c] and the column sums of dY into out_b[row - row_begin] (or NULL): the caller
+// zeroes the gradient buffers once per step.  status: device int raised if a pipeline barrier timed out.
 int nfb_wgrad_bf16(const void* dy, int64_t dy_tile_pitch, int ndy, const void* x, int64_t x_tile_pitch, int nx,
-                   int64_t ntiles, float* part_w, float* part_b, int* status, void* stream) {
-  NFB_REQUIRE(dy && x && part_w && status, "wgrad_bf16: null pointer");
-  NFB_REQUIRE((ndy == 2 || ndy == 4) && (nx == 1 || nx == 2 || nx == 4), "wgrad_bf16: ndy=%d nx=%d", ndy, nx);
-  NFB_REQUIRE(ntiles >= 0 && dy_tile_pitch % 16 == 0 && x_tile_pitch % 16 == 0, "wgrad_bf16: bad pitch");
-  static bool attr_set = false;
-  if (!attr_set) {
-    NFB_CUDA(cudaFuncSetAttribute(nfb::wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::wg::SMEM_BYTES));
-    attr_set = true;
-  }
-  nfb::wg::Args a{(const char*)dy, dy_tile_pitch, ndy, (const char*)x, x_tile_pitch, nx, ntiles, part_w, part_b, status};
-  nfb::wg::wgrad_kernel<<<nfb::sm_count(), nfb::wg::THREADS, nfb::wg::SMEM_BYTES, (cudaStream_t)stream>>>(a);
-  return nfb::check_launch("wgrad_bf16");
-}
-
-int nfb_wgrad_reduce(const float* part, int nparts, int rows, int cols, int cols_valid, float* out, int ld, int col0,
-                     int accumulate, void* stream) {
-  NFB_REQUIRE(part && out && nparts > 0 && rows > 0 && cols > 0 && cols_valid > 0 && cols_valid <= cols, "wgrad_reduce: bad argument");
-  const int64_t n = (int64_t)rows * cols_valid;
-  nfb::wg::wgrad_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part, nparts, rows, cols, cols_valid,
-                                                                                         out, ld, col0, accumulate);
-  return nfb::check_launch("wgrad_reduce");
+                   int64_t ntiles, float* out_w, int ld, int col0, int cols_valid, int row_begin, int row_end,
+                   float* out_b, int* status, void* stream) {
+  nfb::WgradJob j{dy, dy_tile_pitch, x, x_tile_pitch, out_w, out_b, ndy, ndy, nx, ld, col0, cols_valid, row_begin, row_end};
+  return nfb::launch_wgrad_grouped(&j, 1, ntiles, nullptr, status, stream, "wgrad_bf16");
 }
 
 }  // extern "C"

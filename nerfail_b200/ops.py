@@ -484,25 +484,19 @@ def to_tile_image(x: torch.Tensor) -> torch.Tensor:
 
 def wgrad_bf16(dy_img: torch.Tensor, x_img: torch.Tensor, want_bias=True):
     """dy_img [T, ndy, 128, 64] bf16, x_img [T, nx, 128, 64] bf16 (tile images; may be views with a tile pitch) ->
-    (dW [64*ndy, 64*nx] fp32, db [64*ndy] fp32 or None)."""
+    (dW [64*ndy, 64*nx] fp32, db [64*ndy] fp32 or None).  One product of nfb_mlp_bwd_weights' grouped launch."""
     lib = _lib.load()
     T, ndy = dy_img.shape[0], dy_img.shape[1]
     nx = x_img.shape[1]
     assert dy_img.dtype == torch.bfloat16 and x_img.dtype == torch.bfloat16 and x_img.shape[0] == T
     assert dy_img.stride(1) == 8192 and x_img.stride(1) == 8192 and dy_img.stride(3) == 1 and x_img.stride(3) == 1
     dev = dy_img.device
-    parts = int(lib.nfb_wgrad_parts())
-    pw = torch.empty((parts, 64 * ndy, 64 * nx), dtype=torch.float32, device=dev)
-    pb = torch.empty((parts, 64 * ndy), dtype=torch.float32, device=dev) if want_bias else None
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    dW = torch.empty((64 * ndy, 64 * nx), dtype=torch.float32, device=dev)
-    db = torch.empty((64 * ndy,), dtype=torch.float32, device=dev) if want_bias else None
+    dW = torch.zeros((64 * ndy, 64 * nx), dtype=torch.float32, device=dev)
+    db = torch.zeros((64 * ndy,), dtype=torch.float32, device=dev) if want_bias else None
     with torch.cuda.device(dev):
         check(lib.nfb_wgrad_bf16(dy_img.data_ptr(), dy_img.stride(0) * 2, ndy, x_img.data_ptr(), x_img.stride(0) * 2, nx, T,
-                                 ptr(pw), ptr(pb), ptr(status), stream()), "nfb_wgrad_bf16")
-        check(lib.nfb_wgrad_reduce(ptr(pw), parts, 64 * ndy, 64 * nx, 64 * nx, ptr(dW), 64 * nx, 0, 0, stream()), "nfb_wgrad_reduce")
-        if want_bias:
-            check(lib.nfb_wgrad_reduce(ptr(pb), parts, 1, 64 * ndy, 64 * ndy, ptr(db), 64 * ndy, 0, 0, stream()), "nfb_wgrad_reduce")
+                                 ptr(dW), 64 * nx, 0, 64 * nx, 0, 64 * ndy, ptr(db), ptr(status), stream()), "nfb_wgrad_bf16")
     if int(status.item()) != 0:
         raise RuntimeError("nfb_wgrad_bf16: pipeline barrier timed out")
     return dW, db
@@ -520,7 +514,7 @@ def from_tile_image(img: torch.Tensor) -> torch.Tensor:
 
 class FusedMLPTrainFn(torch.autograd.Function):
     """raw = NeRF(rays, z) on tensor cores with autograd: forward = nfb_mlp_fwd_train (saves bf16 activations as tile
-    images), backward = nfb_mlp_bwd_data (dY images) + one nfb_wgrad_bf16 product per weight matrix.
+    images), backward = nfb_mlp_bwd_data (dY images) + nfb_mlp_bwd_weights (all 16 dW products in one grouped launch).
     Gradients flow to the network parameters only (rays / depths are constants of the step, run_nerf.py:394)."""
 
     @staticmethod
@@ -539,6 +533,8 @@ class FusedMLPTrainFn(torch.autograd.Function):
             check(lib.nfb_mlp_fwd_train(fused._h, ptr(rays), ptr(z_vals), R, S, ptr(raw), ptr(act), ptr(mask), stream()),
                   "nfb_mlp_fwd_train")
         ctx.fused, ctx.M, ctx.T = fused, M, T
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.n_params = sum(int(np.prod(sh)) for sh in ctx.shapes)
         ctx.save_for_backward(act, mask)
         return raw
 
@@ -549,33 +545,15 @@ class FusedMLPTrainFn(torch.autograd.Function):
         M, T = ctx.M, ctx.T
         dev = act.device
         g_raw = _f32(g_raw).reshape(M, 4)
-        dy = torch.empty((T, 38, 128, 64), dtype=torch.bfloat16, device=dev)
+        dy = torch.empty((T, 39, 128, 64), dtype=torch.bfloat16, device=dev)
+        grad = torch.zeros(ctx.n_params, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             check(lib.nfb_mlp_bwd_data(ctx.fused._h, ptr(g_raw), M, ptr(mask), ptr(dy), stream()), "nfb_mlp_bwd_data")
-        h = lambda s_: act[:, 4 * s_: 4 * s_ + 4]                     # output of MMA step s_ (h_0..h_7, feature at 8)
-        dY = lambda l: dy[:, 6 + 4 * (7 - l): 10 + 4 * (7 - l)]       # dY of pts_linears.l
-        pe, dirs, hv = act[:, 38:39], act[:, 39:40], act[:, 36:38]
-        grads = []
-        for l in range(8):
-            if l == 0:
-                w, b = wgrad_bf16(dY(0), pe)
-                gw = w[:, :63].contiguous()
-            elif l == 5:
-                wh, b = wgrad_bf16(dY(5), h(4))
-                wp, _ = wgrad_bf16(dY(5), pe, want_bias=False)
-                gw = torch.cat([wp[:, :63], wh], 1)
-            else:
-                gw, b = wgrad_bf16(dY(l), h(l - 1))
-            grads += [gw, b]
-        wf, bv = wgrad_bf16(dy[:, 0:2], h(8))                         # views_linears.0: [feature, dirs]
-        wd, _ = wgrad_bf16(dy[:, 0:2], dirs, want_bias=False)
-        grads += [torch.cat([wf, wd[:, :27]], 1), bv]
-        gwf, gbf = wgrad_bf16(dy[:, 2:6], h(7))                       # feature_linear
-        grads += [gwf, gbf]
-        head = torch.zeros((T * 128, 128), dtype=torch.float32, device=dev)
-        head[:M, :4] = g_raw                                          # columns 0..2 = d/d rgb logits, 3 = d/d sigma
-        head_img = to_tile_image(head)
-        wa, bh = wgrad_bf16(head_img, h(7))                           # row 3 = alpha_linear.weight
-        wr, _ = wgrad_bf16(head_img, hv, want_bias=False)             # rows 0..2 = rgb_linear.weight
-        grads += [wa[3:4].contiguous(), bh[3:4].contiguous(), wr[:3].contiguous(), bh[:3].contiguous()]
+            check(lib.nfb_mlp_bwd_weights(ctx.fused._h, ptr(act), ptr(dy), T, ptr(grad), stream()), "nfb_mlp_bwd_weights")
+        # views of the flat gradient in state_dict order (the order FusedMLPTrainFn.apply received the parameters in)
+        grads, o = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp))
+            grads.append(grad[o:o + n].view(shp))
+            o += n
         return (None, None, None, *grads)

@@ -186,6 +186,30 @@ def test_wgrad_bf16_tile_images(cuda, ntiles, ndy, nx):
     assert float((db.cpu().double() - ref_b).abs().max()) < 1e-4 * float(ref_b.abs().max()) + 1e-3, "db"
 
 
+def test_wgrad_bf16_output_window_accumulates(cuda):
+    """nfb_wgrad_bf16 accumulates rows [row_begin, row_end) x cols_valid columns at (ld, col0) of a larger gradient
+    tensor (how pts_linears.5 / views_linears.0 receive their two column blocks) and leaves everything else alone."""
+    from nerfail_b200 import ops, _lib
+    g = torch.Generator().manual_seed(11)
+    T = 9
+    dy = (torch.randn(T * 128, 256, generator=g) * 0.5).to(torch.bfloat16)
+    x = torch.relu(torch.randn(T * 128, 64, generator=g)).to(torch.bfloat16)
+    dyi, xi = ops.to_tile_image(dy.float().to(cuda)), ops.to_tile_image(x.float().to(cuda))
+    base = torch.randn(100, 319, generator=g).to(cuda)
+    out, ob = base.clone(), torch.full((100,), 2.0, device=cuda)
+    status = torch.zeros(1, dtype=torch.int32, device=cuda)
+    lib = _lib.load()
+    rc = lib.nfb_wgrad_bf16(dyi.data_ptr(), dyi.stride(0) * 2, 4, xi.data_ptr(), xi.stride(0) * 2, 1, T,
+                            out.data_ptr(), 319, 5, 63, 30, 130, ob.data_ptr(), status.data_ptr(), ops.stream())
+    assert rc == 0 and int(status.item()) == 0
+    ref = (dy.double().t() @ x.double())[30:130, :63]
+    exp = base.cpu().double().clone()
+    exp[:, 5:68] += ref
+    assert float((out.cpu().double() - exp).abs().max()) < 1e-4 * float(ref.abs().max()) + 1e-4
+    assert torch.equal(out[:, :5], base[:, :5]) and torch.equal(out[:, 68:], base[:, 68:])
+    assert float((ob.cpu().double() - 2.0 - dy.double().sum(0)[30:130]).abs().max()) < 1e-3
+
+
 def _train_setup(cuda, R=37, S=64, seed=4):
     import nerfail_b200 as nb
     net = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
