@@ -14,7 +14,9 @@
 //              encoded direction 39                                            -> FWD_CHUNKS = 40 per tile
 //   backward : dY_views 0..1, dY_feature 2..5, dY_l (l = 7..0) at 6 + 4 (7 - l), head chunk 38 (columns 0..3 = the upstream
 //              gradient of the rgb logits and of sigma, the rest zero: dY of the two heads) -> BWD_CHUNKS = 39 per tile
-//   masks    : [tile][9][128 rows][8 words]: words of h_0..h_7 (index 0..7) and of the view layer (index 8, 4 words)
+//   masks    : [tile][9][8 words][128 rows]: words of h_0..h_7 (index 0..7) and of the view layer (index 8, 4 words);
+//              word w of a row covers columns 32 w .. 32 w + 31, column 32 w + j = bit 31 - j (a warp stores / loads
+//              128 contiguous bytes)
 
 namespace nfb {
 namespace tr {
@@ -41,7 +43,8 @@ struct TrainArgs {
   float* raw;                     // [M,4] out        (MODE_FWD)
   const float* g_raw;             // [M,4] in         (MODE_BWD)
   char* act_img;                  // [ntiles][40][16 KB]  written by MODE_FWD
-  uint32_t* mask;                 // [ntiles][9][128][8]  written by MODE_FWD, read by MODE_BWD
+  uint32_t* mask;                 // [ntiles][9][8][128]  written by MODE_FWD, read by MODE_BWD
+  int skip;                       // profiling only (NERFAIL_B200_TRAIN_SKIP): bit 0 = no mask stores, bit 1 = no image stores
   char* dy_img;                   // [ntiles][39][16 KB]  written by MODE_BWD
 };
 
@@ -76,6 +79,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t byt
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_but_last() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int MODE>
@@ -282,7 +286,7 @@ mlp_train_kernel(const TrainArgs a) {
         float4 gr = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live) gr = __ldg(reinterpret_cast<const float4*>(a.g_raw) + m);
         gsig = gr.w;
-        const uint2 mw = *reinterpret_cast<const uint2*>(mask_tile + (8 * 128 + row) * 8 + hcol * 2);
+        const uint2 mw = make_uint2(mask_tile[(64 + hcol * 2) * 128 + row], mask_tile[(64 + hcol * 2 + 1) * 128 + row]);
         const uint32_t cb = act + hcol * CHUNK_BYTES;                    // chunk hcol holds view-layer columns hcol*64 ..
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -292,7 +296,7 @@ mlp_train_kernel(const TrainArgs a) {
             const int c = hcol * 64 + u * 8 + j;
             const float t = fmaf(gr.x, sd->w_rgb[0][c], fmaf(gr.y, sd->w_rgb[1][c], gr.z * sd->w_rgb[2][c]));
             const uint32_t word = (u < 4) ? mw.x : mw.y;
-            v[j] = ((word >> ((u & 3) * 8 + j)) & 1u) ? t : 0.f;
+            v[j] = ((word >> (31 - ((u & 3) * 8 + j))) & 1u) ? t : 0.f;
           }
           const uint32_t addr = cb + row * 128 + (((u ^ (row & 7)) & 7) << 4);
           st_shared_v4(addr, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -321,8 +325,12 @@ mlp_train_kernel(const TrainArgs a) {
         full_phase ^= 1;
         tc_fence_after();
         const bool last = (s == nsteps - 1);
-        // the bulk store issued after the previous step must be done reading the activation chunks we overwrite now
-        if (tslot == 0) bulk_wait_read();
+        // Image stores go out in two bulk groups per step: chunks {0, 2} as soon as the first half of the drain has
+        // written them, chunks {1, 3} at the end.  Before overwriting chunks {0, 2} only the older group of the previous
+        // step must be done reading shared memory; the younger one is waited for half a drain later (cc == 2).  The
+        // stores are HBM-bound (64 KB per slot and step), so this doubles the time they have before they stall the drain.
+        const bool wait_all = (MODE == MODE_BWD && s == 0) || (MODE == MODE_FWD && s == 9);   // previous group read chunks 0/1
+        if (tslot == 0) { if (wait_all) bulk_wait_read(); else bulk_wait_read_but_last(); }
         slot_sync();
 
         if (MODE == MODE_FWD && s == 9) {
@@ -342,17 +350,20 @@ mlp_train_kernel(const TrainArgs a) {
               const float4 w0 = reinterpret_cast<const float4*>(sd->w_rgb[0] + col0)[j];
               const float4 w1 = reinterpret_cast<const float4*>(sd->w_rgb[1] + col0)[j];
               const float4 w2 = reinterpret_cast<const float4*>(sd->w_rgb[2] + col0)[j];
-              h[4 * j] = fmaxf(__uint_as_float(v[4 * j]) + b4.x, 0.f);
-              h[4 * j + 1] = fmaxf(__uint_as_float(v[4 * j + 1]) + b4.y, 0.f);
-              h[4 * j + 2] = fmaxf(__uint_as_float(v[4 * j + 2]) + b4.z, 0.f);
-              h[4 * j + 3] = fmaxf(__uint_as_float(v[4 * j + 3]) + b4.w, 0.f);
+              h[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
+              h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+              h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {                      // mask bit first (sign of the pre-activation), then relu
+                mword = __funnelshift_l(__float_as_uint(h[4 * j + t]), mword, 1);
+                h[4 * j + t] = fmaxf(h[4 * j + t], 0.f);
+              }
               r0 = fmaf(h[4 * j], w0.x, r0); r0 = fmaf(h[4 * j + 1], w0.y, r0); r0 = fmaf(h[4 * j + 2], w0.z, r0); r0 = fmaf(h[4 * j + 3], w0.w, r0);
               r1 = fmaf(h[4 * j], w1.x, r1); r1 = fmaf(h[4 * j + 1], w1.y, r1); r1 = fmaf(h[4 * j + 2], w1.z, r1); r1 = fmaf(h[4 * j + 3], w1.w, r1);
               r2 = fmaf(h[4 * j], w2.x, r2); r2 = fmaf(h[4 * j + 1], w2.y, r2); r2 = fmaf(h[4 * j + 2], w2.z, r2); r2 = fmaf(h[4 * j + 3], w2.w, r2);
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mword |= (h[j] > 0.f ? 1u : 0u) << j;
-            mask_tile[(8 * 128 + row) * 8 + hcol * 2 + cc] = mword;
+            if (!(a.skip & 1)) mask_tile[(64 + hcol * 2 + cc) * 128 + row] = ~mword;
             const uint32_t cb = act + hcol * CHUNK_BYTES;                // view-layer columns hcol*64 .. -> chunk hcol
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -382,15 +393,29 @@ mlp_train_kernel(const TrainArgs a) {
         const bool relu = (MODE == MODE_FWD) ? (s < 8) : (s >= 1);       // bwd: step 0 outputs dY_feature (no activation)
         const int mask_layer = (MODE == MODE_FWD) ? s : 8 - s;           // bwd step b masks with relu'(h_{8-b})
         uint4 mw4 = make_uint4(0u, 0u, 0u, 0u);
-        if (MODE == MODE_BWD && relu) mw4 = *reinterpret_cast<const uint4*>(mask_tile + (mask_layer * 128 + row) * 8 + hcol * 4);
+        if (MODE == MODE_BWD && relu) {
+          const uint32_t* mp = mask_tile + (mask_layer * 8 + hcol * 4) * 128 + row;
+          mw4 = make_uint4(mp[0], mp[128], mp[256], mp[384]);
+        }
         float sig_acc = 0.f;
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
+          if (cc == 2) {
+            fence_proxy_async();
+            if (tslot == 0) bulk_wait_read();
+            slot_sync();                               // chunks 0 and 2 are final; chunks 1 and 3 may be overwritten
+            if (tslot == 0 && !(a.skip & 2)) {
+              char* dst = (MODE == MODE_FWD) ? act_tile + (int64_t)(s * 4) * CHUNK_BYTES : dy_tile + (int64_t)dy_chunk0(s) * CHUNK_BYTES;
+              bulk_s2g(dst, act, CHUNK_BYTES);
+              bulk_s2g(dst + 2 * CHUNK_BYTES, act + 2 * CHUNK_BYTES, CHUNK_BYTES);
+              bulk_commit();
+            }
+          }
           const int col0 = hcol * 128 + cc * 32;
           uint32_t v[32];
           tmem_ld32(tmem_row + col0, v);
           float4 b4[8];
-          if (MODE == MODE_FWD || s == 1) {
+          if (MODE == MODE_BWD && s == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) b4[j] = reinterpret_cast<const float4*>(bias_s + col0)[j];
           }
@@ -399,8 +424,9 @@ mlp_train_kernel(const TrainArgs a) {
           if (MODE == MODE_FWD) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              h[4 * j] = __uint_as_float(v[4 * j]) + b4[j].x; h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4[j].y;
-              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4[j].z; h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4[j].w;
+              const float4 b = reinterpret_cast<const float4*>(bias_s + col0)[j];     // loaded at use: 32 fewer live registers
+              h[4 * j] = __uint_as_float(v[4 * j]) + b.x; h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z; h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
             }
             if (s == 7) {
 #pragma unroll
@@ -411,10 +437,12 @@ mlp_train_kernel(const TrainArgs a) {
               }
             }
             if (relu) {
+              // relu mask = complement of the gathered sign bits, one funnel shift per column: column j of the word is
+              // bit 31 - j (an exactly zero pre-activation counts as active: measure-zero deviation from relu'(0) = 0)
               uint32_t mword = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) mword |= (h[j] > 0.f ? 1u : 0u) << j;
-              mask_tile[(mask_layer * 128 + row) * 8 + hcol * 4 + cc] = mword;
+              for (int j = 0; j < 32; ++j) mword = __funnelshift_l(__float_as_uint(h[j]), mword, 1);
+              if (!(a.skip & 1)) mask_tile[(mask_layer * 8 + hcol * 4 + cc) * 128 + row] = ~mword;
             }
           } else {
             // backward: dX (+ g_sigma * w_alpha for the layer-7 activation), then relu'
@@ -431,7 +459,7 @@ mlp_train_kernel(const TrainArgs a) {
             if (relu) {
               const uint32_t mword = cc == 0 ? mw4.x : cc == 1 ? mw4.y : cc == 2 ? mw4.z : mw4.w;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) h[j] = ((mword >> j) & 1u) ? h[j] : 0.f;
+              for (int j = 0; j < 32; ++j) h[j] = ((mword >> (31 - j)) & 1u) ? h[j] : 0.f;
             }
           }
           const uint32_t cb = act + (col0 >> 6) * CHUNK_BYTES;
@@ -461,11 +489,11 @@ mlp_train_kernel(const TrainArgs a) {
         fence_proxy_async();
         slot_sync();                                   // activation chunks (and the bias row) of this step are final
         if (tslot == 0) {
-          if (MODE == MODE_FWD) {
-            bulk_s2g(act_tile + (int64_t)(s * 4) * CHUNK_BYTES, act, 4 * CHUNK_BYTES);
-            if (s == 8) bulk_s2g(act_tile + (int64_t)IMG_DIR * CHUNK_BYTES, pe, CHUNK_BYTES);
-          } else {
-            bulk_s2g(dy_tile + (int64_t)dy_chunk0(s) * CHUNK_BYTES, act, 4 * CHUNK_BYTES);
+          if (!(a.skip & 2)) {
+            char* dst = (MODE == MODE_FWD) ? act_tile + (int64_t)(s * 4) * CHUNK_BYTES : dy_tile + (int64_t)dy_chunk0(s) * CHUNK_BYTES;
+            bulk_s2g(dst + CHUNK_BYTES, act + CHUNK_BYTES, CHUNK_BYTES);
+            bulk_s2g(dst + 3 * CHUNK_BYTES, act + 3 * CHUNK_BYTES, CHUNK_BYTES);
+            if (MODE == MODE_FWD && s == 8) bulk_s2g(act_tile + (int64_t)IMG_DIR * CHUNK_BYTES, pe, CHUNK_BYTES);
           }
           bulk_commit();
         }

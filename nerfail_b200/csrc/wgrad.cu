@@ -7,7 +7,9 @@
 // 128 rows x 128 bytes with the 128-byte swizzle (exactly the shared-memory image of an A operand).  Read as a matrix
 // with K = rows and MN = the 64 columns, such a chunk IS the canonical MN-major SWIZZLE_128B operand layout, so both
 // dY^T (A, M = n_out) and X (B, N = k_in) are fed to tcgen05.mma straight from bulk copies, no transposition.
-//   stage    = 64 rows of every chunk of one tile (8 KB slices, chunk pitch 8 KB inside the stage), 3-deep ring
+//   stage    = 64 rows of every chunk of one tile (8 KB slices, chunk pitch 8 KB inside the stage); the 192 KB ring
+//              holds 3 (64 KB stages) to 8 (24 KB stages) of them, so narrow products keep as many bytes in flight
+//              as wide ones (with a fixed 3-deep ring their CTAs were latency-bound and finished 1.5x late)
 //   MMA      = M 128 (two dY chunks) x N 64*nx x K 16 rows, fp32 accumulators for both M halves stay in TMEM (<= 512
 //              columns) across all tiles of the CTA
 //   bias     = 4 CUDA-core warps sum the dY slices of each stage out of shared memory
@@ -24,8 +26,9 @@ constexpr int ROWS_PER_STAGE = 64;
 constexpr int SLICE_BYTES = ROWS_PER_STAGE * 128;       // 8 KB: 64 rows of one chunk
 constexpr int MAX_CHUNKS = 8;                           // 4 dY + 4 X
 constexpr int STAGE_BYTES = MAX_CHUNKS * SLICE_BYTES;   // 64 KB
-constexpr int NSTAGE = 3;
-constexpr int SM_BAR = NSTAGE * STAGE_BYTES;
+constexpr int RING_BYTES = 3 * STAGE_BYTES;             // 192 KB ring, cut into as many stages as the job's stage size allows
+constexpr int NSTAGE = 8;                               // upper bound (stage of 24 KB: a 2-chunk dY against a 1-chunk X)
+constexpr int SM_BAR = RING_BYTES;
 constexpr int SM_SCRATCH = SM_BAR + 256;                  // 4 epilogue warps x [32][33] floats (transpose for coalesced reductions)
 constexpr int SMEM_BYTES = SM_SCRATCH + 4 * 32 * 33 * 4;
 constexpr int THREADS = 32 * 10;                        // warp 0 producer, 1 MMA/TMEM, 2-5 epilogue, 6-9 bias sums
@@ -112,6 +115,10 @@ struct Args {
 // (cost of a tile of job j = ndy_real + nx chunks).  A CTA therefore works on one to three consecutive jobs, keeps a
 // job's whole dW in TMEM while it walks that job's tiles and flushes it once per job.
 struct Segment { int64_t lo, hi; };
+__device__ __forceinline__ int ring_stages(int stage_bytes) {
+  const int n = RING_BYTES / stage_bytes;
+  return n < NSTAGE ? n : NSTAGE;
+}
 __device__ __forceinline__ Segment job_segment(const Args& a, int j, int64_t cost_before, int64_t cost_total) {
   const int64_t W = a.ntiles * cost_total;
   const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
@@ -164,39 +171,53 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
 
   if (warp == 0) {
     // ================= producer: 64-row slices of every chunk of a tile, one stage per half tile =================
-    int64_t it = 0, cost_before = 0;
+    int64_t cost_before = 0;
+    uint32_t pmask = 0;                                  // bit s = parity of the next use of stage index s
+    bool first = true;
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
       cost_before += jb.ndy_real + jb.nx;
+      if (sg.hi <= sg.lo) continue;
+      const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
+      const int nst = ring_stages(stage_bytes);
+      if (!first)                                        // the ring is re-cut: every stage of the previous job must be free
+        for (int s2 = 0; s2 < NSTAGE; ++s2) mbar_wait(EMPTY_B(s2), ((pmask >> s2) & 1u) ^ 1u, flag);
+      first = false;
+      int st = 0;
       for (int64_t tile = sg.lo; tile < sg.hi; ++tile) {
-        for (int half = 0; half < 2; ++half, ++it) {
-          const int st = (int)(it % NSTAGE);
-          const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t ph = (pmask >> st) & 1u;
           mbar_wait(EMPTY_B(st), ph ^ 1, flag);
+          const uint32_t dst = base + st * stage_bytes;
+          const uint32_t full = FULL_B(st);
+          pmask ^= 1u << st;
+          st = (st + 1 == nst) ? 0 : st + 1;
           if (elect_one()) {
-            mbar_arrive_expect_tx(FULL_B(st), (jb.ndy + jb.nx) * SLICE_BYTES);
-            const uint32_t dst = base + st * STAGE_BYTES;
+            mbar_arrive_expect_tx(full, stage_bytes);
             for (int c = 0; c < jb.ndy; ++c) {
               const char* src = c < jb.ndy_real ? jb.dy + tile * jb.dy_pitch + (int64_t)c * 16384 + half * SLICE_BYTES : a.zero;
-              bulk_g2s(dst + c * SLICE_BYTES, src, SLICE_BYTES, FULL_B(st));
+              bulk_g2s(dst + c * SLICE_BYTES, src, SLICE_BYTES, full);
             }
             for (int c = 0; c < jb.nx; ++c)
               bulk_g2s(dst + (jb.ndy + c) * SLICE_BYTES, jb.x + tile * jb.x_pitch + (int64_t)c * 16384 + half * SLICE_BYTES,
-                       SLICE_BYTES, FULL_B(st));
+                       SLICE_BYTES, full);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer: dW (both 128-row halves) accumulates in TMEM over the job's tiles =================
-    int64_t it = 0, cost_before = 0;
-    uint32_t seg = 0;
+    int64_t cost_before = 0;
+    uint32_t seg = 0, pmask = 0;
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
       cost_before += jb.ndy_real + jb.nx;
       if (sg.hi <= sg.lo) continue;
+      const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
+      const int nst_ring = ring_stages(stage_bytes);
+      int st = 0;
       const uint32_t idesc = idesc_mn(64 * jb.nx);
       const int mhalves = jb.ndy / 2;
       if (seg > 0) {                                   // the previous job's accumulators must have been drained
@@ -204,12 +225,13 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       const int64_t nst = (sg.hi - sg.lo) * 2;
-      for (int64_t i = 0; i < nst; ++i, ++it) {
-        const int st = (int)(it % NSTAGE);
-        const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
-        mbar_wait(FULL_B(st), ph, flag);
+      for (int64_t i = 0; i < nst; ++i) {
+        mbar_wait(FULL_B(st), (pmask >> st) & 1u, flag);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sbase = base + st * STAGE_BYTES;
+        const uint32_t sbase = base + st * stage_bytes;
+        const uint32_t empty = EMPTY_B(st);
+        pmask ^= 1u << st;
+        st = (st + 1 == nst_ring) ? 0 : st + 1;
         if (elect_one()) {
           for (int mh = 0; mh < mhalves; ++mh) {
 #pragma unroll
@@ -223,7 +245,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
                   :: "r"(tmem_base + mh * 256), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
             }
           }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(EMPTY_B(st)) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(empty) : "memory");
           if (i == nst - 1)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(DONE_B) : "memory");
         }
@@ -234,23 +256,26 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     // ================= bias sums: warp (6 + c) owns dY chunk c; lane = (row group of 4) x (16-byte unit = 8 columns) ====
     const int c = warp - 6;
     const int unit = lane & 7, rg = lane >> 3;
-    int64_t it = 0, cost_before = 0;
+    int64_t cost_before = 0;
+    uint32_t pmask = 0;
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
       cost_before += jb.ndy_real + jb.nx;
       if (sg.hi <= sg.lo) continue;
+      const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
+      const int nst_ring = ring_stages(stage_bytes);
+      int st = 0;
       const bool mine = jb.out_b && c < jb.ndy_real;
       float acc8[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc8[q] = 0.f;
       const int64_t nst = (sg.hi - sg.lo) * 2;
-      for (int64_t i = 0; i < nst; ++i, ++it) {
-        const int st = (int)(it % NSTAGE);
-        const uint32_t ph = (uint32_t)((it / NSTAGE) & 1);
-        mbar_wait(FULL_B(st), ph, flag);
+      for (int64_t i = 0; i < nst; ++i) {
+        mbar_wait(FULL_B(st), (pmask >> st) & 1u, flag);
+        const uint32_t empty = EMPTY_B(st);
         if (mine) {
-          const uint8_t* sl = smem + st * STAGE_BYTES + c * SLICE_BYTES;
+          const uint8_t* sl = smem + st * stage_bytes + c * SLICE_BYTES;
           for (int r = rg; r < ROWS_PER_STAGE; r += 4) {
             const uint4 v = *reinterpret_cast<const uint4*>(sl + r * 128 + (((unit ^ (r & 7)) & 7) << 4));
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -262,7 +287,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(EMPTY_B(st));
+        if (lane == 0) mbar_arrive(empty);
+        pmask ^= 1u << st;
+        st = (st + 1 == nst_ring) ? 0 : st + 1;
       }
       if (mine) {
 #pragma unroll

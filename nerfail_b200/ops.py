@@ -527,7 +527,7 @@ class FusedMLPTrainFn(torch.autograd.Function):
         T = int(lib.nfb_mlp_train_tiles(M))
         dev = rays.device
         act = torch.empty((T, 40, 128, 64), dtype=torch.bfloat16, device=dev)
-        mask = torch.empty((T, 9, 128, 8), dtype=torch.int32, device=dev)
+        mask = torch.empty((T, 9, 8, 128), dtype=torch.int32, device=dev)
         raw = torch.empty((R, S, 4), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             check(lib.nfb_mlp_fwd_train(fused._h, ptr(rays), ptr(z_vals), R, S, ptr(raw), ptr(act), ptr(mask), stream()),

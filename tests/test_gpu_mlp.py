@@ -240,8 +240,8 @@ def test_fused_train_forward_saves_exact_activations(cuda):
         got = flat[:, s * 256:(s + 1) * 256]
         assert torch.equal(got, want), f"saved activation of step {s}"
         if s < 8:
-            words = mask[:, s].reshape(-1, 8)[:M].cpu().numpy().astype(np.uint32)
-            bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(M, 256).astype(bool)
+            words = mask[:, s].permute(0, 2, 1).reshape(-1, 8)[:M].cpu().numpy().astype(np.uint32)    # [tile][word][row] -> rows x words
+            bits = ((words[:, :, None] >> (31 - np.arange(32, dtype=np.uint32))[None, None, :]) & 1).reshape(M, 256).astype(bool)   # column j = bit 31 - j
             assert np.array_equal(bits, (dbg > 0).cpu().numpy()), f"relu mask of step {s}"
     # encoded point / direction chunks against the reference encoding (bf16 rounding of the kernel's own PE)
     pts = (rays[:, None, 0:3] + rays[:, None, 3:6] * z[..., None]).reshape(-1, 3).cpu()
