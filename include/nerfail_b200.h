@@ -152,6 +152,17 @@ NFB_API int nfb_wgrad_bf16(const void* dy, int64_t dy_tile_pitch, int ndy, const
                            int64_t ntiles, float* out_w, int ld, int col0, int cols_valid, int row_begin, int row_end,
                            float* out_b, int* status, void* stream);
 
+/* Fused multi-tensor Adam (no amsgrad / weight decay), one launch for every parameter tensor of both networks.
+ * replaces: optimizer.step() of torch.optim.Adam at run_nerf.py:792 (created at :213, betas (0.9, 0.999), eps 1e-8);
+ * the learning-rate decay of :796-800 is a host scalar passed as lr.  step = 1 for the first update (bias corrections
+ * 1 - beta^step).  grad_scale multiplies every gradient first (1/world_size of a data-parallel mean, else 1).
+ * State layout = torch.optim.Adam's state_dict (exp_avg, exp_avg_sq per parameter), so reference checkpoints resume.  */
+typedef struct nfb_adam_tensor {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64_t numel;
+} nfb_adam_tensor;
+NFB_API int nfb_adam_step(const nfb_adam_tensor* tensors, int count, int64_t step, double lr, double beta1, double beta2,
+                          double eps, double grad_scale, void* stream);
+
 /* Alpha compositing. replaces: run_nerf.py:262-305 (raw2outputs) and, when pts_max != NULL,
  * nerf_to_coord.py:418-421 (arg-max-weight point o + d*z[argmax], first maximum wins).
  * raw [R,S,4], z_vals [R,S], rays_d [R,3] (taken from rays+3 with pitch ray_pitch floats), noise [R,S] or NULL.
@@ -190,6 +201,19 @@ NFB_API int nfb_hierarchical(const float* z_coarse, const float* weights, const 
  * float32, :148-151; C < 2^24 required) and/or out_idx_i32 [Q,8].                                      */
 NFB_API int nfb_knn8(const float* query, int64_t Q, const float* cand, int64_t C,
              float* out_dist, float* out_idx, int32_t* out_idx_i32, void* stream);
+
+/* The same exact 8-NN through a uniform grid (identical outputs; ~1000x fewer distance evaluations on surface points).
+ * nfb_knn_grid_build buckets the candidates once (they are the fixed P base views of a data set,
+ * create_index_and_dist.py:96-108) into a 256^3 Morton-ordered grid: origin bbox_min (host, 3 floats), cell edge h with
+ * bbox_min + 256 h >= bbox_max; sorted [C,4] fp32, cell_start [nfb_knn_grid_cells() + 1] int32, workspace
+ * [nfb_knn_grid_cells() + 4096] int32.  nfb_knn8_grid answers queries against it; margin_abs = absolute slack of the
+ * pruning bound (4e-6 x the largest |coordinate| is ample); stats: optional device uint64 += distance evaluations. */
+NFB_API int64_t nfb_knn_grid_cells(void);
+NFB_API int nfb_knn_grid_build(const float* cand, int64_t C, const float* bbox_min_host, float h, float* sorted,
+                               int32_t* cell_start, int32_t* workspace, void* stream);
+NFB_API int nfb_knn8_grid(const float* query, int64_t Q, const float* sorted, const int32_t* cell_start,
+                          const float* bbox_min_host, float h, float margin_abs, float* out_dist, float* out_idx,
+                          int32_t* out_idx_i32, unsigned long long* stats, void* stream);
 
 /* replaces: model/GaussNet.py:169-186 (create_gauss_w.forward).
  * dist_idx [B,2,HW,8] -> i_w [B,2,HW,8] (ch0 = weights, ch1 = indices copied).                        */

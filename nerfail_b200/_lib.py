@@ -44,11 +44,15 @@ SIGNATURES = {
     "nfb_linear_bwd_weight_workspace": (c_i64, [c_i64, c_int, c_int]),
     "nfb_mlp_bwd_weights": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "nfb_wgrad_bf16": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "nfb_adam_step": (c_int, [c_ptr, c_int, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_ptr]),
     "nfb_composite_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_composite_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_sample_pdf": (c_int, [c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "nfb_hierarchical": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_knn8": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_knn_grid_cells": (c_i64, []),
+    "nfb_knn_grid_build": (c_int, [c_ptr, c_i64, c_ptr, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_knn8_grid": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, C.c_float, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_gauss_weights": (c_int, [c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr]),
     "nfb_gauss_gather_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_gauss_scatter_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_i64, c_ptr, c_ptr]),

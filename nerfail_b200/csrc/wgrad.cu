@@ -18,6 +18,8 @@
 //              contiguous ranges, one range per CTA (see job_segment)
 // HBM-bound by design: 1 KB per row and layer against 2*256*256 FLOP.
 #include "common.cuh"
+#include <stdlib.h>
+#include <vector>
 
 namespace nfb {
 namespace wg {
@@ -109,10 +111,11 @@ struct Args {
   int64_t ntiles;
   const char* zero;                     // 16 KB of zeros (only read when some job has ndy_real < ndy)
   int* flag;
+  unsigned long long* dbg;              // profiling only (NERFAIL_B200_WGRAD_DBG=1): per CTA globaltimer at start / end
 };
 
 // Work split: the (job, tile) pairs, jobs in table order, are cut into gridDim.x contiguous ranges of equal HBM cost
-// (cost of a tile of job j = ndy_real + nx chunks).  A CTA therefore works on one to three consecutive jobs, keeps a
+// (cost of a tile of job j = ndy + nx chunks moved into shared memory, zero padding included).  A CTA therefore works on one to three consecutive jobs, keeps a
 // job's whole dW in TMEM while it walks that job's tiles and flushes it once per job.
 struct Segment { int64_t lo, hi; };
 __device__ __forceinline__ int ring_stages(int stage_bytes) {
@@ -123,7 +126,7 @@ __device__ __forceinline__ Segment job_segment(const Args& a, int j, int64_t cos
   const int64_t W = a.ntiles * cost_total;
   const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
   const int64_t base = cost_before * a.ntiles;
-  const int64_t c = a.job[j].ndy_real + a.job[j].nx;
+  const int64_t c = a.job[j].ndy + a.job[j].nx;
   auto cut = [&](int64_t w) -> int64_t {
     if (w <= base) return 0;
     const int64_t t = (w - base + c - 1) / c;
@@ -167,7 +170,12 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   int64_t cost_total = 0;
-  for (int j = 0; j < a.njobs; ++j) cost_total += a.job[j].ndy_real + a.job[j].nx;
+  for (int j = 0; j < a.njobs; ++j) cost_total += a.job[j].ndy + a.job[j].nx;
+  if (a.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[2 * blockIdx.x] = t;
+  }
 
   if (warp == 0) {
     // ================= producer: 64-row slices of every chunk of a tile, one stage per half tile =================
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
-      cost_before += jb.ndy_real + jb.nx;
+      cost_before += jb.ndy + jb.nx;
       if (sg.hi <= sg.lo) continue;
       const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
       const int nst = ring_stages(stage_bytes);
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
-      cost_before += jb.ndy_real + jb.nx;
+      cost_before += jb.ndy + jb.nx;
       if (sg.hi <= sg.lo) continue;
       const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
       const int nst_ring = ring_stages(stage_bytes);
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
-      cost_before += jb.ndy_real + jb.nx;
+      cost_before += jb.ndy + jb.nx;
       if (sg.hi <= sg.lo) continue;
       const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
       const int nst_ring = ring_stages(stage_bytes);
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
-      cost_before += jb.ndy_real + jb.nx;
+      cost_before += jb.ndy + jb.nx;
       if (sg.hi <= sg.lo) continue;
       mbar_wait(DONE_B, seg & 1, flag);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -347,6 +355,11 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (a.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.dbg[2 * blockIdx.x + 1] = t;
+  }
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(512) : "memory");
 }
 
@@ -371,13 +384,30 @@ int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const 
                 s.row_begin < s.row_end && s.ld >= s.col0 + s.cols_valid, "%s: job %d: bad output window", what, j);
     a.job[j] = wg::Job{(const char*)s.dy, s.dy_pitch, (const char*)s.x, s.x_pitch, s.out_w, s.out_b,
                        s.ndy, s.ndy_real, s.nx, s.ld, s.col0, s.cols_valid, s.row_begin, s.row_end};
-    cost += s.ndy_real + s.nx;
+    cost += s.ndy + s.nx;
   }
   a.njobs = njobs; a.ntiles = ntiles; a.zero = (const char*)zero16k; a.flag = status;
   NFB_CUDA(cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
   int64_t grid = sm_count();
   if ((int64_t)njobs * ntiles < grid) grid = (int64_t)njobs * ntiles;
+  static const bool dbg = []() { const char* e = getenv("NERFAIL_B200_WGRAD_DBG"); return e && e[0] == '1'; }();
+  if (dbg) NFB_CUDA(cudaMalloc(&a.dbg, sizeof(unsigned long long) * 2 * grid));
   wg::wgrad_kernel<<<(unsigned)grid, wg::THREADS, wg::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  if (dbg) {     // per-CTA duration against its first job: shows whether the equal-cost split is equal-time
+    std::vector<unsigned long long> t(2 * grid);
+    NFB_CUDA(cudaMemcpy(t.data(), a.dbg, sizeof(unsigned long long) * 2 * grid, cudaMemcpyDeviceToHost));
+    cudaFree(a.dbg);
+    unsigned long long t0 = ~0ull;
+    for (int64_t b = 0; b < grid; ++b) t0 = t[2 * b] < t0 ? t[2 * b] : t0;
+    const int64_t W = ntiles * cost;
+    for (int64_t b = 0; b < grid; ++b) {
+      const int64_t w0 = W * b / grid;
+      int64_t cb = 0; int j0 = 0;
+      for (int j = 0; j < njobs; ++j) { const int64_t c = jobs[j].ndy + jobs[j].nx; if (w0 < (cb + c) * ntiles) { j0 = j; break; } cb += c; }
+      fprintf(stderr, "wgrad cta %3lld first job %2d (ndy %d/%d nx %d)  start %8.1f us  end %8.1f us\n", (long long)b, j0, jobs[j0].ndy_real,
+              jobs[j0].ndy, jobs[j0].nx, (t[2 * b] - t0) / 1e3, (t[2 * b + 1] - t0) / 1e3);
+    }
+  }
   return check_launch(what);
 }
 

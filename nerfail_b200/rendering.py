@@ -15,6 +15,7 @@ import torch
 
 from . import nerf, ops
 from .nerf import NeRF, get_embedder
+from .optim import Adam
 
 DEBUG = False
 
@@ -289,7 +290,7 @@ def create_nerf(args, device=None):
         grad_vars += list(model_fine.parameters())
 
     network_query_fn = NetworkQuery(embed_fn, embeddirs_fn, args.netchunk)
-    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    optimizer = Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))       # fused multi-tensor kernel, torch.optim.Adam state_dict
 
     start = 0
     basedir, expname = getattr(args, 'basedir', None), getattr(args, 'expname', None)

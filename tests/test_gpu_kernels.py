@@ -272,3 +272,53 @@ def test_knn8_ties_duplicates_and_ragged(cuda):
     # exactly 8 candidates, one query
     d, i = ops.knn8(T(qry[:1]).to(cuda), T(cand[:8]).to(cuda))
     assert sorted(i.cpu().numpy()[0].tolist()) == list(range(8))
+
+
+def test_fused_adam_matches_torch_adam_and_shares_its_state_dict(cuda):
+    """nfb_adam_step against torch.optim.Adam on the CPU (the reference's optimizer, run_nerf.py:213/:792) over several
+    steps with a decaying learning rate (:796-800); then the two optimizers swap state_dicts (checkpoint compatibility,
+    :228) and keep agreeing.  Tolerance: ulp-level differences of the fused fp32 update (2e-6 relative on the parameters)."""
+    import nerfail_b200 as nb
+    g = torch.Generator().manual_seed(3)
+    shapes = [(256, 63), (256,), (1, 256), (1,), (3, 128), (128, 283), (4097,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    got_p = [torch.nn.Parameter(p.detach().clone().to(cuda)) for p in ref_p]
+    ref_o = torch.optim.Adam(ref_p, lr=5e-4, betas=(0.9, 0.999))
+    got_o = nb.Adam(got_p, lr=5e-4, betas=(0.9, 0.999))
+
+    def one_step(i):
+        for a, b in zip(ref_p, got_p):
+            a.grad = torch.randn(a.shape, generator=g) * (10.0 ** float(torch.randint(-4, 2, (1,), generator=g)))
+            b.grad = a.grad.to(cuda)
+        v0 = [p._version for p in got_p]
+        ref_o.step(); got_o.step()
+        assert all(p._version > v for p, v in zip(got_p, v0)), "the fused step must bump tensor versions (weight re-pack trigger)"
+        lr = nb.decayed_lrate(5e-4, 250, i + 1)
+        nb.set_lrate(ref_o, lr); nb.set_lrate(got_o, lr)
+
+    def check():
+        for a, b in zip(ref_p, got_p):
+            assert torch.allclose(b.detach().cpu(), a.detach(), rtol=2e-6, atol=2e-7), float((b.detach().cpu() - a.detach()).abs().max())
+        for a, b in zip(ref_p, got_p):
+            sa, sb = ref_o.state[a], got_o.state[b]
+            assert float(sa["step"]) == float(sb["step"])
+            assert torch.allclose(sb["exp_avg"].cpu(), sa["exp_avg"], rtol=1e-5, atol=1e-6 * float(sa["exp_avg"].abs().max()))
+            assert torch.allclose(sb["exp_avg_sq"].cpu(), sa["exp_avg_sq"], rtol=1e-5, atol=1e-6 * float(sa["exp_avg_sq"].abs().max()))
+
+    for i in range(4):
+        one_step(i)
+    check()
+    # swap checkpoints: torch state into the fused optimizer and the fused state into torch
+    sd_ref, sd_got = ref_o.state_dict(), got_o.state_dict()
+    assert sd_ref["param_groups"][0].keys() == sd_got["param_groups"][0].keys()
+    got_o.load_state_dict(sd_ref)
+    ref_o.load_state_dict({"state": {k: {kk: (vv.cpu() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} for k, v in sd_got["state"].items()},
+                           "param_groups": sd_got["param_groups"]})
+    for i in range(4, 7):
+        one_step(i)
+    check()
+    # parameters without a gradient are skipped, like torch
+    got_p[0].grad = None
+    before = got_p[0].detach().clone()
+    got_o.step()
+    assert torch.equal(got_p[0].detach(), before)
