@@ -10,10 +10,11 @@ from .rendering import (render, render_rays, run_network, raw2outputs, batchify,
                      create_nerf, NetworkQuery)
 from .gauss import gauss_net, create_gauss_w, knn_index_and_dist
 from .optim import Adam, decayed_lrate, set_lrate
+from .pipeline import SpatialPointSet, render_points, build_attack_inputs
 
 __all__ = [
     "NeRF", "Embedder", "get_embedder", "get_rays", "get_rays_np", "ndc_rays", "sample_pdf", "img2mse", "mse2psnr",
     "to8b", "render", "render_rays", "run_network", "raw2outputs", "batchify", "batchify_rays", "render_path",
-    "create_nerf", "NetworkQuery", "gauss_net", "create_gauss_w", "knn_index_and_dist", "Adam", "decayed_lrate", "set_lrate",
+    "create_nerf", "NetworkQuery", "gauss_net", "create_gauss_w", "knn_index_and_dist", "Adam", "decayed_lrate", "set_lrate", "SpatialPointSet", "render_points", "build_attack_inputs",
 ]
 __version__ = "0.1.0"

@@ -96,7 +96,7 @@ constexpr int KG_SCAN_BLOCK = 4096;                // elements per scan block (2
 struct KnnGridParams { float ox, oy, oz, h, inv_h, margin_abs; };
 
 __host__ __device__ __forceinline__ uint32_t kg_spread(uint32_t v) {      // 8 bits -> every third bit
-  v = (v | (v << 16)) & 0x0300F00Fu;
+  v = (v | (v << 16)) & 0x030000FFu;
   v = (v | (v << 8)) & 0x0300F00Fu;
   v = (v | (v << 4)) & 0x030C30C3u;
   v = (v | (v << 2)) & 0x09249249u;

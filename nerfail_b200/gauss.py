@@ -5,6 +5,8 @@ weighting, the epsilon clip / composite and their backward run in libnerfail_b20
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -115,7 +117,12 @@ class gauss_net(nn.Module):
         return x, x_rgba, cla, ori_f, ori_cla
 
 
-def knn_index_and_dist(query_hw3: torch.Tensor, base_points: torch.Tensor) -> torch.Tensor:
+def knn_index_and_dist(query_hw3: torch.Tensor, base_points) -> torch.Tensor:
     """One view of create_index_and_dist.py:110-151: float32 [2,H,W,8] = cat([dist, idx]) for every pixel's
-    3-D point against the [P*H*W,3] base-view points."""
-    return ops.knn8_dist_idx(query_hw3, base_points)
+    3-D point against the [P*H*W,3] base-view points.  `base_points` is the point tensor or, to amortise the grid
+    build over the views of a data set, an `ops.KnnGrid` made from it; NERFAIL_B200_KNN=brute selects the plain scan."""
+    if isinstance(base_points, ops.KnnGrid):
+        return base_points.query_dist_idx(query_hw3)
+    if os.environ.get("NERFAIL_B200_KNN", "grid").lower() == "brute":
+        return ops.knn8_dist_idx(query_hw3, base_points)
+    return ops.KnnGrid(base_points).query_dist_idx(query_hw3)

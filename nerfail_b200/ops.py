@@ -357,6 +357,59 @@ def knn8(query: torch.Tensor, cand: torch.Tensor):
     return dist, idx
 
 
+class KnnGrid:
+    """Exact 8-NN accelerator for a fixed candidate set (the P base views of a data set, create_index_and_dist.py:96-108):
+    256^3 Morton grid over the candidates' bounding box, built once on the device (nfb_knn_grid_build); `query` returns
+    exactly what `knn8` returns (same fp32 distance expression, ties to the lower index)."""
+
+    def __init__(self, cand: torch.Tensor):
+        _require_cuda(cand)
+        lib = _lib.load()
+        self.cand = _f32(cand).reshape(-1, 3)
+        self.C = self.cand.shape[0]
+        dev = self.cand.device
+        finite = torch.isfinite(self.cand).all(dim=1, keepdim=True)
+        big = torch.finfo(torch.float32).max
+        lo = torch.where(finite, self.cand, torch.full_like(self.cand, big)).min(0).values.cpu().numpy().astype(np.float32)
+        hi = torch.where(finite, self.cand, torch.full_like(self.cand, -big)).max(0).values.cpu().numpy().astype(np.float32)
+        extent = float(np.max(hi - lo))
+        if not np.isfinite(extent) or extent <= 0.0:
+            extent = 1.0
+            lo = np.zeros(3, np.float32) if not np.all(np.isfinite(lo)) else lo
+        self.h = float(np.float32(extent * (1.0 + 1e-4) / 256.0))          # 256 cells cover the longest axis with slack
+        self.lo = np.ascontiguousarray(lo, dtype=np.float32)
+        self.margin_abs = float(4e-6 * max(float(np.abs(lo).max()), float(np.abs(hi).max()), 1e-30))
+        cells = int(lib.nfb_knn_grid_cells())
+        self.sorted = torch.empty((self.C, 4), dtype=torch.float32, device=dev)
+        self.cell_start = torch.empty(cells + 1, dtype=torch.int32, device=dev)
+        work = torch.empty(cells + 4096, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.nfb_knn_grid_build(ptr(self.cand), self.C, self.lo.ctypes.data, self.h, ptr(self.sorted), ptr(self.cell_start),
+                                         ptr(work), stream()), "nfb_knn_grid_build")
+
+    def _run(self, q, dist, idx_f, idx_i, stats=None):
+        with torch.cuda.device(q.device):
+            check(_lib.load().nfb_knn8_grid(ptr(q), q.shape[0], ptr(self.sorted), ptr(self.cell_start), self.lo.ctypes.data, self.h,
+                                            self.margin_abs, ptr(dist), ptr(idx_f), ptr(idx_i), ptr(stats), stream()), "nfb_knn8_grid")
+
+    def query(self, query: torch.Tensor, stats: torch.Tensor | None = None):
+        """(dist [Q,8] fp32, idx [Q,8] int32); stats: optional int64 device scalar accumulating distance evaluations."""
+        _require_cuda(query)
+        q = _f32(query).reshape(-1, 3)
+        dist = torch.empty((q.shape[0], 8), dtype=torch.float32, device=q.device)
+        idx = torch.empty((q.shape[0], 8), dtype=torch.int32, device=q.device)
+        self._run(q, dist, None, idx, stats)
+        return dist, idx
+
+    def query_dist_idx(self, query_hw3: torch.Tensor) -> torch.Tensor:
+        """float32 [2,H,W,8] = cat([dist, idx]), the reference's on-disk layout (create_index_and_dist.py:148-151)."""
+        H, W = query_hw3.shape[0], query_hw3.shape[1]
+        q = _f32(query_hw3).reshape(-1, 3)
+        out = torch.empty((2, H * W, 8), dtype=torch.float32, device=q.device)
+        self._run(q, out[0], out[1], None)
+        return out.reshape(2, H, W, 8)
+
+
 def knn8_dist_idx(query_hw3: torch.Tensor, cand: torch.Tensor) -> torch.Tensor:
     """The reference's on-disk layout: float32 [2,H,W,8] = cat([dist, idx]) (create_index_and_dist.py:148-151)."""
     H, W = query_hw3.shape[0], query_hw3.shape[1]

@@ -274,6 +274,52 @@ def test_knn8_ties_duplicates_and_ragged(cuda):
     assert sorted(i.cpu().numpy()[0].tolist()) == list(range(8))
 
 
+def test_knn_grid_equals_brute_force_bit_for_bit(cuda):
+    """The grid-accelerated search must return exactly the brute-force result (indices AND distances): golden set and
+    tie lattice against the oracle; a 150 k-point noisy sphere surface with outliers against the brute-force kernel
+    (itself pinned to the oracle above), with queries on the surface, far outside the bounding box and at candidates."""
+    from nerfail_b200 import ops
+    g = golden("knn.npz")
+    q, c = g["query"].reshape(-1, 3), g["cand"]
+    d_ref, i_ref = go.knn8_exact(q, c)
+    grid = ops.KnnGrid(T(c).to(cuda))
+    d, i = grid.query(T(q).to(cuda))
+    assert np.array_equal(i.cpu().numpy(), i_ref) and np.array_equal(d.cpu().numpy(), d_ref)
+    packed = grid.query_dist_idx(T(g["query"]).to(cuda)).cpu().numpy()
+    assert packed.shape == (2, 10, 16, 8) and np.array_equal(packed[1].reshape(-1, 8).astype(np.int32), i_ref)
+
+    rng = np.random.default_rng(4)
+    cand = rng.integers(0, 4, size=(5000, 3)).astype(np.float32)      # exact ties and ~78-fold duplicates per lattice site
+    qry = rng.integers(0, 4, size=(301, 3)).astype(np.float32)
+    d_ref, i_ref = go.knn8_exact(qry, cand)
+    d, i = ops.KnnGrid(T(cand).to(cuda)).query(T(qry).to(cuda))
+    assert np.array_equal(i.cpu().numpy(), i_ref), "ties must resolve to the lowest candidate index"
+    assert np.array_equal(d.cpu().numpy(), d_ref)
+
+    n = 150_000
+    dirs = rng.normal(size=(n, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    cand = (dirs * (1.0 + 0.002 * rng.normal(size=(n, 1)))).astype(np.float32)
+    cand[:200] = rng.uniform(-6, 6, size=(200, 3)).astype(np.float32)          # background-like outliers stretch the box
+    cand[200:260] = cand[260:320]                                                # duplicates with different indices
+    qd = rng.normal(size=(30_000, 3)); qd /= np.linalg.norm(qd, axis=1, keepdims=True)
+    qry = (qd * (1.0 + 0.002 * rng.normal(size=(30_000, 1)))).astype(np.float32)
+    qry[:500] = rng.uniform(-20, 20, size=(500, 3)).astype(np.float32)           # far outside the candidates' bounding box
+    qry[500:1000] = cand[1000:1500]                                              # zero distances
+    qry[1000:1500] = rng.uniform(-6, 6, size=(500, 3)).astype(np.float32)        # empty space inside the box
+    cg, qg = T(cand).to(cuda), T(qry).to(cuda)
+    d_bf, i_bf = ops.knn8(qg, cg)
+    grid = ops.KnnGrid(cg)
+    stats = torch.zeros(1, dtype=torch.int64, device=cuda)
+    d, i = grid.query(qg, stats)
+    assert torch.equal(i, i_bf), f"{int((i != i_bf).any(1).sum())} queries differ from the brute-force search"
+    assert torch.equal(d, d_bf)
+    d_ref, i_ref = go.knn8_exact(qry[:1600:8], cand)
+    assert np.array_equal(i.cpu().numpy()[:1600:8], i_ref) and np.array_equal(d.cpu().numpy()[:1600:8], d_ref)
+    pruning = qry.shape[0] * n / float(stats.item())
+    print(f"grid kNN pruning factor {pruning:.0f}x ({float(stats.item()) / qry.shape[0]:.0f} distance evaluations per query)")
+    assert pruning > 20
+
+
 def test_fused_adam_matches_torch_adam_and_shares_its_state_dict(cuda):
     """nfb_adam_step against torch.optim.Adam on the CPU (the reference's optimizer, run_nerf.py:213/:792) over several
     steps with a decaying learning rate (:796-800); then the two optimizers swap state_dicts (checkpoint compatibility,

@@ -178,3 +178,44 @@ def test_full_size_view_properties(cuda):
         ref = no.render_ray_batch(rays[pick.to(cuda)].cpu(), sd_c, sd_f)
     got = rgb.reshape(-1, 3)[pick.to(cuda)].cpu()
     assert psnr(got.numpy(), ref["rgb_map"].numpy()) > 40.0
+
+
+def test_on_device_index_weight_pipeline_and_reference_file_formats(cuda, tmp_path):
+    """render(with_pts_max) -> 8-NN -> Gaussian weights -> gauss_net without the disk, against the oracle
+    chain on the SAME rendered points (knn8_exact -> gaussian_weights -> gauss_forward), and the reference's three file
+    formats (coords/NNN.npy, index_and_dist/i.pth, index_and_weight/i.pth) round-trip bit-exactly."""
+    import nerfail_b200 as nb
+    from nerfail_b200 import pipeline
+    from oracle import gauss_oracle as go
+    H = W = 20
+    K, _ = synth.intrinsics(H, W)
+    poses = [torch.tensor(p) for p in synth.camera_ring(5)]
+    _, kw = make_kwargs(cuda)
+    kwr = dict(kw, near=2., far=6.)
+    sps, w_idx = nb.build_attack_inputs(H, W, K, poses[:3], poses[3:], kwr, chunk=1024, save_dir=str(tmp_path))
+    assert w_idx.shape == (2, 2, H, W, 8) and sps.points.shape == (3 * H * W, 3)
+    base = sps.points.cpu().numpy()
+    for i in range(2):
+        pts = pipeline.load_points_npy(str(tmp_path / "coords" / f"{i:03d}.npy"), cuda)
+        assert pts.shape == (H, W, 3) and pts.dtype == torch.float32
+        d_ref, i_ref = go.knn8_exact(pts.cpu().numpy().reshape(-1, 3), base)
+        di = pipeline.load_index_and_dist(str(tmp_path / "index_and_dist" / f"{i}.pth"), cuda)
+        assert di.shape == (2, H, W, 8) and di.dtype == torch.float32
+        assert np.array_equal(di[1].cpu().numpy().reshape(-1, 8).astype(np.int32), i_ref)
+        assert np.array_equal(di[0].cpu().numpy().reshape(-1, 8), d_ref)
+        iw = pipeline.load_index_and_weight(str(tmp_path / "index_and_weight" / f"{i}.pth"), cuda)
+        assert torch.equal(iw, w_idx[i])
+        ref_iw = go.gaussian_weights(di.cpu().unsqueeze(0), 0.02)[0]
+        assert torch.allclose(iw.cpu(), ref_iw, rtol=2e-6, atol=1e-7)
+    # reading the same files back through the file-based constructor gives the same point set
+    sps2 = nb.SpatialPointSet.from_npy([str(tmp_path / "coords" / f"{i:03d}.npy") for i in range(2)], cuda)
+    assert sps2.shape == (2, H, W)
+    # and the batch feeds gauss_net like the reference's weight_and_index_list
+    g = torch.Generator().manual_seed(0)
+    spatial = (torch.randn(3, H, W, 4, generator=g) * 5).to(cuda)
+    spatial[..., 3] = 255.0
+    ori = torch.randint(0, 256, (2, H, W, 4), generator=g, dtype=torch.uint8).to(cuda)
+    net = nb.gauss_net(cuda, 0.02, None, "my_model", epsilon=32)
+    x, x_rgba = net.perturbed(spatial, w_idx, ori)
+    x_ref, x_rgba_ref, _ = go.gauss_forward(spatial.cpu(), w_idx.cpu(), ori.cpu(), 32)
+    assert torch.allclose(x.cpu(), x_ref, rtol=1e-4, atol=1e-3) and torch.allclose(x_rgba.cpu(), x_rgba_ref, rtol=1e-4, atol=1e-3)
