@@ -240,6 +240,7 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
         return loss
 
     def time_train(n_iter):
+        nonlocal train_step
         train_step()
         torch.cuda.synchronize()
         if world > 1:
@@ -254,10 +255,25 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
 
     ar_bytes = int(sum(p_.numel() for p_ in params_c + params_f) * 4)
     ms32 = time_train(2)
+    opt = nb.Adam(params_c + params_f, lr=5e-4, betas=(0.9, 0.999))      # run_nerf.py:213; fused multi-tensor kernel
+    plain_step = train_step
+
+    def train_step_adam():                                               # run_nerf.py:776-800: backward, step, lr decay
+        loss = plain_step()
+        opt.step()
+        nb.set_lrate(opt, nb.decayed_lrate(5e-4, 250, int(opt.state[params_c[0]]["step"].item())))
+        return loss
     prev = os.environ.get("NERFAIL_B200_TRAIN")
     os.environ["NERFAIL_B200_TRAIN"] = "bf16"       # fused tensor-core forward (saves activations) + dgrad chain + wgrad GEMMs
     try:
         ms16 = time_train(5)
+        sd0 = [p_.detach().clone() for p_ in params_c + params_f]
+        train_step = train_step_adam
+        ms16_adam = time_train(5)
+        train_step = plain_step
+        with torch.no_grad():                                            # restore the weights the other measurements use
+            for p_, w_ in zip(params_c + params_f, sd0):
+                p_.copy_(w_)
     finally:
         if prev is None:
             os.environ.pop("NERFAIL_B200_TRAIN", None)
@@ -267,10 +283,42 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
     out["retraining_step"] = {"metric": "NeRF fwd+bwd rays/s (4096-ray batch, coarse+fine, bf16 tensor-core training kernels)",
                               "value": N_rand / (ms16 / 1e3), "unit": "rays/s", "ms_per_step": ms16, "rays_per_rank": int(e - b),
                               "dtype": "bf16", "optimizer_step": False, "allreduce_bytes": ar_bytes, "scaling": "strong",
+                              "with_fused_adam_and_weight_repack": {"ms_per_step": ms16_adam, "value": N_rand / (ms16_adam / 1e3), "unit": "rays/s"},
                               "algorithmic_TFLOPs": flop_step / world / (ms16 / 1e3) / 1e12,
                               "fp32_layer_kernels": {"value": N_rand / (ms32 / 1e3), "unit": "rays/s", "ms_per_step": ms32, "dtype": "f32"}}
     for p_ in params_c + params_f:
         p_.grad = None
+
+    # ---- 8-NN precompute of one view (create_index_and_dist.py:110-151) on rendered geometry ----
+    if world == 1:
+        from nerfail_b200 import pipeline
+        poses = synth.camera_ring(8)
+        kwr = {k: v for k, v in kw.items()}
+        kwr.update(near=2.0, far=6.0)
+        base = torch.stack([pipeline.render_points(H, W, K, torch.tensor(poses[i][:3, :4]), 1024, **kwr) for i in (0, 3, 5)], 0)
+        qpts = pipeline.render_points(H, W, K, torch.tensor(poses[1][:3, :4]), 1024, **kwr)
+        cand = base.reshape(-1, 3).contiguous()
+
+        def timed(fn, n):
+            fn(); torch.cuda.synchronize()
+            a, b_ = ev(), ev()
+            a.record()
+            for _ in range(n):
+                r = fn()
+            b_.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b_) / n, r
+
+        ms_build, grid = timed(lambda: ops.KnnGrid(cand), 2)
+        stats = torch.zeros(1, dtype=torch.int64, device=dev)
+        ms_grid, (d_g, i_g) = timed(lambda: grid.query(qpts.reshape(-1, 3), stats), 3)
+        evals = float(stats.item()) / 4.0
+        ms_brute, (d_b, i_b) = timed(lambda: ops.knn8(qpts.reshape(-1, 3), cand), 1)
+        pairs = float(qpts.numel() // 3) * float(cand.shape[0])
+        out["knn_view"] = {"metric": "exact 8-NN of one 800x800 view against P=3 base views (1.92 M candidates)",
+                           "grid_ms": ms_grid, "grid_build_ms": ms_build, "brute_force_ms": ms_brute,
+                           "identical_to_brute_force": bool(torch.equal(i_g, i_b) and torch.equal(d_g, d_b)),
+                           "pruning_factor": pairs / max(evals, 1.0), "brute_force_pairs_per_s": pairs / (ms_brute / 1e3),
+                           "speedup": ms_brute / ms_grid}
     return out
 
 
