@@ -6,6 +6,7 @@
 // (lane = sample within the chunk, so every global access is a fully coalesced 128/512-byte request)
 // and the exclusive transmittance product is a warp shuffle scan carried from chunk to chunk.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nfb {
 
@@ -53,7 +54,8 @@ __device__ __forceinline__ float warp_rscan_add(float v, int lane) {
   return v;
 }
 
-__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+// 1 / y and __frcp_rn(y) are both the correctly rounded reciprocal: identical bits, no division slow path
+__device__ __forceinline__ float sigmoidf(float x) { return __frcp_rn(1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(256)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
@@ -113,6 +115,101 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
         if (q != q) disp[r] = q;                   // keep the reference's NaN
       }
       if (pts_max) {                               // nerf_to_coord.py:397 + :421 : o + d * z
+        const float* o = d - 3;
+        pts_max[(int64_t)r * 3]     = __fadd_rn(__ldg(o),     __fmul_rn(dx, best_z));
+        pts_max[(int64_t)r * 3 + 1] = __fadd_rn(__ldg(o + 1), __fmul_rn(dy, best_z));
+        pts_max[(int64_t)r * 3 + 2] = __fadd_rn(__ldg(o + 2), __fmul_rn(dz, best_z));
+      }
+    }
+  }
+}
+
+// Same arithmetic with the chunk loop unrolled (NCH = ceil(S / 32) known at compile time): all of a ray's loads are in
+// flight at once, the gap to the next depth comes from a shuffle instead of a second load, and the NCH chunk-local
+// scans are independent; only the product of the chunk totals is a serial chain.  Bit-identical to the loop form
+// (same per-chunk scan order, same carry products) and ~2x faster: the loop form exposed one load latency plus one
+// 5-step shuffle scan per chunk on the critical path.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+composite_fwd_unrolled_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
+                              int ray_pitch, const float* __restrict__ noise, int R, int S, int white,
+                              float* __restrict__ rgb_map, float* __restrict__ disp, float* __restrict__ acc_out,
+                              float* __restrict__ weights, float* __restrict__ depth_out, float* __restrict__ pts_max) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < R; r += gridDim.x * warps_per_block) {
+    const float* d = rays_d + (int64_t)r * ray_pitch;
+    const float dx = __ldg(d), dy = __ldg(d + 1), dz = __ldg(d + 2);
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const int64_t base = (int64_t)r * S;
+    float4 rw[NCH];
+    float zz[NCH], nz[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int i = (j << 5) + lane;
+      const bool valid = i < S;
+      rw[j] = valid ? ld_stream4(reinterpret_cast<const float4*>(raw) + base + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      zz[j] = valid ? __ldg(z + base + i) : 0.f;
+      nz[j] = (valid && noise) ? __ldg(noise + base + i) : 0.f;
+    }
+    float alpha[NCH], incl[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int i = (j << 5) + lane;
+      const bool valid = i < S;
+      float znext = __shfl_down_sync(FULL, zz[j], 1);
+      const float zfirst_next = __shfl_sync(FULL, zz[j + 1 < NCH ? j + 1 : j], 0);
+      if (lane == 31) znext = zfirst_next;
+      const float gap = (i + 1 < S) ? __fsub_rn(znext, zz[j]) : 1e10f;                 // :277-278
+      const float dist = __fmul_rn(gap, dnorm);                                        // :280
+      const float sig = fmaxf(rw[j].w + nz[j], 0.f);
+      alpha[j] = valid ? 1.f - expf(-__fmul_rn(sig, dist)) : 0.f;                      // :275
+      const float t = valid ? (1.f - alpha[j]) + 1e-10f : 1.f;                         // :295
+      incl[j] = warp_scan_mul(t, lane);
+    }
+    float carry = 1.f, acc = 0.f, dep = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    float best_w = -INFINITY, best_z = 0.f;
+    int best_i = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int i = (j << 5) + lane;
+      float excl = __shfl_up_sync(FULL, incl[j], 1);
+      if (lane == 0) excl = 1.f;
+      const float T = carry * excl;
+      carry *= __shfl_sync(FULL, incl[j], 31);
+      const float w = alpha[j] * T;
+      if (i < S) {
+        weights[base + i] = w;
+        acc += w;
+        dep += w * zz[j];
+        cr += w * sigmoidf(rw[j].x);
+        cg += w * sigmoidf(rw[j].y);
+        cb += w * sigmoidf(rw[j].z);
+        if (w > best_w) { best_w = w; best_i = i; best_z = zz[j]; }
+      }
+    }
+    acc = warp_sum(acc); dep = warp_sum(dep);
+    cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+    if (pts_max) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ow = __shfl_xor_sync(FULL, best_w, o);
+        int oi = __shfl_xor_sync(FULL, best_i, o);
+        float oz = __shfl_xor_sync(FULL, best_z, o);
+        if (ow > best_w || (ow == best_w && oi < best_i)) { best_w = ow; best_i = oi; best_z = oz; }
+      }
+    }
+    if (lane == 0) {
+      if (white) { const float bg = 1.f - acc; cr += bg; cg += bg; cb += bg; }
+      if (rgb_map) { rgb_map[(int64_t)r * 3] = cr; rgb_map[(int64_t)r * 3 + 1] = cg; rgb_map[(int64_t)r * 3 + 2] = cb; }
+      if (acc_out) acc_out[r] = acc;
+      if (depth_out) depth_out[r] = dep;
+      if (disp) {
+        const float q = dep / acc;
+        disp[r] = 1.f / fmaxf(1e-10f, q);
+        if (q != q) disp[r] = q;
+      }
+      if (pts_max) {
         const float* o = d - 3;
         pts_max[(int64_t)r * 3]     = __fadd_rn(__ldg(o),     __fmul_rn(dx, best_z));
         pts_max[(int64_t)r * 3 + 1] = __fadd_rn(__ldg(o + 1), __fmul_rn(dy, best_z));
@@ -234,8 +331,20 @@ int nfb_composite_fwd(const float* raw, const float* z_vals, const float* rays_d
   NFB_REQUIRE(raw && z_vals && rays_d && weights, "composite_fwd: raw, z_vals, rays_d and weights are required");
   NFB_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "composite_fwd: raw must be 16-byte aligned");
   if (R == 0) return NFB_OK;
-  nfb::composite_fwd_kernel<<<nfb::composite_grid(R), 256, 0, (cudaStream_t)stream>>>(
-      raw, z_vals, rays_d, ray_pitch, noise, R, S, white_bkgd, rgb_map, disp, acc, weights, depth, pts_max);
+  const int grid = nfb::composite_grid(R);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NFB_LAUNCH_FWD(NCH)                                                                                  \
+  nfb::composite_fwd_unrolled_kernel<NCH><<<grid, 256, 0, st>>>(raw, z_vals, rays_d, ray_pitch, noise, R, S, \
+      white_bkgd, rgb_map, disp, acc, weights, depth, pts_max)
+  static const bool loop_form = []() { const char* e = getenv("NERFAIL_B200_COMPOSITE_LOOP"); return e && e[0] == '1'; }();
+  if (loop_form || S > 256)
+    nfb::composite_fwd_kernel<<<grid, 256, 0, st>>>(raw, z_vals, rays_d, ray_pitch, noise, R, S, white_bkgd, rgb_map, disp, acc,
+                                                    weights, depth, pts_max);
+  else if (S <= 64) NFB_LAUNCH_FWD(2);
+  else if (S <= 128) NFB_LAUNCH_FWD(4);
+  else if (S <= 192) NFB_LAUNCH_FWD(6);
+  else NFB_LAUNCH_FWD(8);
+#undef NFB_LAUNCH_FWD
   return nfb::check_launch("composite_fwd");
 }
 

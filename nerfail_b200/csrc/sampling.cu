@@ -107,7 +107,28 @@ __device__ __forceinline__ void build_cdf(const float* __restrict__ w, int nw, f
   }
   for (int i = lane; i < nw; i += 32) cdf[i + 1] = __fdiv_rn(__fadd_rn(__ldg(w + i), 1e-5f), total);
   __syncwarp();
-  if (lane == 0) {                                 // ATen's CPU cumsum: sequential, double accumulator, fp32 outputs
+  // ATen's CPU cumsum: sequential, double accumulator, every prefix rounded to fp32.  When each pdf value is >= 2^-29 all
+  // partial sums (< 2) are multiples of 2^-52, i.e. EXACT in double, so the order of the additions cannot matter and a
+  // warp scan of per-lane blocks yields the same bits as the sequential loop; otherwise (weights spanning > 2^29) lane 0
+  // runs the sequential loop.  (The sequential loop on one lane was 60 % of this kernel's time.)
+  const int per = (nw + 31) >> 5;
+  const int b = lane * per, e = min(b + per, nw);
+  double part = 0.0;
+  float mn = INFINITY;
+  for (int i = b; i < e; ++i) { const float p = cdf[i + 1]; part += (double)p; mn = fminf(mn, p); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+  if (mn >= 1.862645149230957e-09f && total == total) {         // 2^-29
+    double incl = part;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    double run = incl - part;
+    for (int i = b; i < e; ++i) { run += (double)cdf[i + 1]; cdf[i + 1] = (float)run; }
+    if (lane == 0) cdf[0] = 0.f;
+  } else if (lane == 0) {
     double run = 0.0;
     cdf[0] = 0.f;
     for (int i = 1; i <= nw; ++i) { run += (double)cdf[i]; cdf[i] = (float)run; }
@@ -115,20 +136,32 @@ __device__ __forceinline__ void build_cdf(const float* __restrict__ w, int nw, f
   __syncwarp();
 }
 
+// 32-bit shared-window addressing for the search loops: with generic pointers into the dynamic shared-memory window ptxas
+// re-derives the window base (S2R SR_CgaCtaId + LEA) inside every loop iteration, 13 instructions per search step.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+
 // torch.searchsorted(cdf, u, right=True) then the gather / lerp of :227-241.
-__device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins, int nb, float u, int* ind_out) {
-  int lo = 0, hi = nb;                 // first index with cdf[idx] > u
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+__device__ __forceinline__ float invert_cdf(uint32_t cdf, uint32_t bins, int nb, float u, int* ind_out) {
+  // first index with cdf[idx] > u = number of leading knots that are not > u; branch-free descent with a trip count that
+  // depends on nb only (the while-loop form cost ~16 instructions per step in divergent BSSY/BSYNC regions)
+  int lo = 0;
+  for (int step = 1 << (31 - __clz(nb)); step > 0; step >>= 1) {
+    const int np = lo + step;
+    if (np <= nb && !(lds_f32(cdf + 4 * (np - 1)) > u)) lo = np;
   }
   if (ind_out) *ind_out = lo;
   const int below = max(0, lo - 1), above = min(nb - 1, lo);
-  const float c0 = cdf[below], c1 = cdf[above];
+  const float c0 = lds_f32(cdf + 4 * below), c1 = lds_f32(cdf + 4 * above);
   float denom = __fsub_rn(c1, c0);
   if (denom < 1e-5f) denom = 1.f;
   const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
-  const float b0 = bins[below], b1 = bins[above];
+  const float b0 = lds_f32(bins + 4 * below), b1 = lds_f32(bins + 4 * above);
   return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
 }
 
@@ -147,7 +180,7 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
     for (int k = lane; k < N; k += 32) {
       const float uk = u ? __ldg(u + (int64_t)r * N + k) : linspace01(k, N);
       int ind;
-      const float s = invert_cdf(cdf, sb, nb, uk, &ind);
+      const float s = invert_cdf(smem_addr(cdf), smem_addr(sb), nb, uk, &ind);
       samples[(int64_t)r * N + k] = s;
       if (inds) inds[(int64_t)r * N + k] = ind;
     }
@@ -176,6 +209,7 @@ hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict_
   float* zc = sb + nb;
   float* zs = zc + Sc;
   float* out = zs + P;
+  const uint32_t cdf_a = smem_addr(cdf), sb_a = smem_addr(sb), zc_a = smem_addr(zc), zs_a = smem_addr(zs), out_a = smem_addr(out);
   for (int r = blockIdx.x * wpb + wib; r < R; r += gridDim.x * wpb) {
     for (int i = lane; i < Sc; i += 32) zc[i] = __ldg(z_coarse + (int64_t)r * Sc + i);
     for (int i = N + lane; i < P; i += 32) zs[i] = INFINITY;
@@ -185,7 +219,7 @@ hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict_
     float sum = 0.f;
     for (int k = lane; k < N; k += 32) {
       const float uk = u ? __ldg(u + (int64_t)r * N + k) : linspace01(k, N);
-      const float s = invert_cdf(cdf, sb, nb, uk, nullptr);
+      const float s = invert_cdf(cdf_a, sb_a, nb, uk, nullptr);
       zs[k] = s;
       sum += s;
       if (z_samples) z_samples[(int64_t)r * N + k] = s;
@@ -202,7 +236,23 @@ hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict_
     // verify (one pass) and only sort if an inversion exists, since the rank merge below needs sorted runs.
     bool unsorted = false;
     for (int k = lane; k + 1 < N; k += 32) unsorted |= zs[k] > zs[k + 1];
-    if (__any_sync(FULL, unsorted)) {
+    unsorted = __any_sync(FULL, unsorted);
+    if (unsorted && !u) {
+      // deterministic u: inversions are isolated adjacent pairs at bin boundaries; a few odd-even transposition rounds
+      // repair them for ~60 instructions each instead of the 28-pass bitonic network (which was 3/4 of this kernel)
+      for (int round = 0; round < 4 && unsorted; ++round) {
+        bool swapped = false;
+        for (int par = 0; par < 2; ++par) {
+          for (int k = 2 * lane + par; k + 1 < N; k += 64) {
+            const float a = zs[k], b = zs[k + 1];
+            if (a > b) { zs[k] = b; zs[k + 1] = a; swapped = true; }
+          }
+          __syncwarp();
+        }
+        unsorted = __any_sync(FULL, swapped);      // a round without swaps means the run is sorted
+      }
+    }
+    if (unsorted) {
       for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
           for (int i = lane; i < P; i += 32) {
@@ -218,17 +268,24 @@ hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict_
       }
     }
     // merge by rank
+    const int step_n = 1 << (31 - __clz(N)), step_c = 1 << (31 - __clz(Sc));
     for (int i = lane; i < Sc; i += 32) {
-      const float v = zc[i];
-      int lo = 0, hi = N;                    // number of new samples strictly below v
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (zs[mid] < v) lo = mid + 1; else hi = mid; }
-      out[i + lo] = v;
+      const float v = lds_f32(zc_a + 4 * i);
+      int lo = 0;                            // number of new samples strictly below v
+      for (int step = step_n; step > 0; step >>= 1) {
+        const int np = lo + step;
+        if (np <= N && lds_f32(zs_a + 4 * (np - 1)) < v) lo = np;
+      }
+      sts_f32(out_a + 4 * (i + lo), v);
     }
     for (int k = lane; k < N; k += 32) {
-      const float v = zs[k];
-      int lo = 0, hi = Sc;                   // number of coarse depths <= v
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (zc[mid] <= v) lo = mid + 1; else hi = mid; }
-      out[k + lo] = v;
+      const float v = lds_f32(zs_a + 4 * k);
+      int lo = 0;                            // number of coarse depths <= v
+      for (int step = step_c; step > 0; step >>= 1) {
+        const int np = lo + step;
+        if (np <= Sc && lds_f32(zc_a + 4 * (np - 1)) <= v) lo = np;
+      }
+      sts_f32(out_a + 4 * (k + lo), v);
     }
     __syncwarp();
     for (int i = lane; i < Sf; i += 32) z_fine[(int64_t)r * Sf + i] = out[i];
