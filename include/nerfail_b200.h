@@ -104,7 +104,11 @@ NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, co
  * image dy_img [tiles][39][16 KB] (chunk 38 = the upstream gradient itself, dY of the two heads).
  * nfb_mlp_bwd_weights computes every weight / bias gradient of the network from the two images in ONE grouped launch
  * (16 products dW = dY^T X, see nfb_wgrad_bf16) and ACCUMULATES them into grad [nfb_mlp_param_count] in state_dict
- * order: zero grad once per step.  tiles = nfb_mlp_train_tiles(M).  A barrier time-out is reported by nfb_mlp_status. */
+ * order: zero grad once per step.  tiles = nfb_mlp_train_tiles(M).  A barrier time-out is reported by nfb_mlp_status.
+ * nfb_mlp_bwd = both of them as two CONCURRENT kernels on disjoint SMs (the loss.backward() of run_nerf.py:791 for one
+ * network): the weight-gradient CTAs consume each tile's dY out of L2 as soon as the data-gradient CTAs have published it
+ * through ready [tiles] int32 (workspace, zeroed by the call), so dY is never read back from HBM.  Same outputs as the two
+ * separate calls up to fp32 summation order; the work after the call on `stream` is ordered behind both kernels. */
 NFB_API int64_t nfb_mlp_train_tiles(int64_t M);
 NFB_API int nfb_mlp_fwd_train(const nfb_mlp_t* h, const float* rays, const float* z_vals, int R, int S, float* raw,
                               void* act_img, uint32_t* mask, void* stream);
@@ -112,6 +116,8 @@ NFB_API int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, 
                              void* stream);
 NFB_API int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_img, int64_t ntiles, float* grad,
                                 void* stream);
+NFB_API int nfb_mlp_bwd(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_t* mask, const void* act_img,
+                        void* dy_img, float* grad, int* ready, void* stream);
 
 /* Profiling aid: the full forward (mode 1) while CTA 0 records a timeline of its barrier waits into
  * trace [3 roles][2048 events][4] uint64 = (tag, clock begin, clock end, aux); roles: 0 weight producer, 1 MMA warp,

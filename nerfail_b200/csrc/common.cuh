@@ -48,8 +48,10 @@ struct WgradJob {
   int ndy, ndy_real, nx;
   int ld, col0, cols_valid, row_begin, row_end;
 };
+// ready / job_need / consumer_ctas: consumer mode (see wgrad.cu): dY is produced concurrently by mlp_train_kernel<BWD>, which
+// publishes ready[tile] = number of its store groups that have landed; job j may load a tile once ready[tile] >= job_need[j].
 int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const void* zero16k, int* status, void* stream,
-                         const char* what);
+                         const char* what, const int* ready = nullptr, const signed char* job_need = nullptr, int consumer_ctas = 0);
 
 // ---- device ------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;

@@ -85,6 +85,8 @@ struct nfb_mlp {
   int cslot;                 // index into the __constant__ c_side table of this device
   int* abort_flag;           // set by the kernel if a barrier wait timed out
   void* zero16k;             // 16 KB of zeros: the padding dY chunk of the head weight-gradient products
+  cudaStream_t side_stream;  // second stream + fork/join events: the weight-gradient kernel of nfb_mlp_bwd runs next to
+  cudaEvent_t ev_fork, ev_join;   // the data-gradient kernel on its own SMs
   int device;
   int64_t n_params;
 };
@@ -854,6 +856,7 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
                      "(got D=%d W=%d input_ch=%d input_ch_views=%d skip=%d)", D, W, input_ch, input_ch_views, skip);
   nfb_mlp* h = new nfb_mlp();
   h->image = nullptr; h->image_t = nullptr; h->side = nullptr; h->abort_flag = nullptr; h->zero16k = nullptr; h->cslot = -1;
+  h->side_stream = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
   h->n_params = nfb::param_layout().total;
   cudaError_t e = cudaGetDevice(&h->device);
   if (e == cudaSuccess && (h->device < 0 || h->device >= 64)) { delete h; return nfb::fail(NFB_E_UNSUPPORTED, "mlp_create: device index out of range"); }
@@ -871,6 +874,9 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
   if (e == cudaSuccess) e = cudaMemset(h->abort_flag, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&h->zero16k, nfb::CHUNK_BYTES);
   if (e == cudaSuccess) e = cudaMemset(h->zero16k, 0, nfb::CHUNK_BYTES);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e == cudaSuccess)
@@ -881,6 +887,9 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
     e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e != cudaSuccess) {
     cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag); cudaFree(h->zero16k);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     release_cslot(h->device, h->cslot);
     delete h;
     return nfb::fail(NFB_E_CUDA, "mlp_create: %s", cudaGetErrorString(e));
@@ -909,6 +918,9 @@ int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* st
 int nfb_mlp_destroy(nfb_mlp_t* h) {
   if (!h) return NFB_OK;
   cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag); cudaFree(h->zero16k);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   release_cslot(h->device, h->cslot);
   delete h;
   return NFB_OK;
@@ -977,12 +989,13 @@ int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const floa
 }
 
 // ---- training (bf16 tensor-core forward that saves activations, and the data-gradient chain) ----
-static int train_launch(int mode, const nfb_mlp_t* h, nfb::tr::TrainArgs& a, void* stream) {
+static int train_launch(int mode, const nfb_mlp_t* h, nfb::tr::TrainArgs& a, void* stream, int max_groups = 0) {
   static const int skip = []() { const char* e = getenv("NERFAIL_B200_TRAIN_SKIP"); return e ? atoi(e) : 0; }();
   a.skip = skip;
   const int64_t rows_per_unit = 2 * nfb::TILE_M * 2;
   const int64_t nunits = (a.M + rows_per_unit - 1) / rows_per_unit;
   int groups = nfb::sm_count() / 2;
+  if (max_groups > 0 && max_groups < groups) groups = max_groups;
   if (nunits < groups) groups = (int)nunits;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(groups * 2));
@@ -1025,33 +1038,91 @@ int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, const ui
   return train_launch(nfb::tr::MODE_BWD, h, a, stream);
 }
 
+// The 16 products dW = dY^T X (+ bias sums) of one network over the saved images, gradient in state_dict order.
+// need[j] = value of the data-gradient kernel's per-tile ready counter from which job j's dY chunks of that tile are
+// complete (mlp_train.inl: 1 = input stage (view-layer dY + head chunk), b + 2 = output of backward step b).
+static int wgrad_jobs(const void* act_img, const void* dy_img, float* grad, nfb::WgradJob* jobs, signed char* need) {
+  using namespace nfb;
+  const ParamLayout pl = param_layout();
+  const int64_t ap = (int64_t)tr::FWD_CHUNKS * CHUNK_BYTES, dp = (int64_t)tr::BWD_CHUNKS * CHUNK_BYTES;
+  auto A = [&](int chunk) { return (const void*)((const char*)act_img + (int64_t)chunk * CHUNK_BYTES); };
+  auto D = [&](int chunk) { return (const void*)((const char*)dy_img + (int64_t)chunk * CHUNK_BYTES); };
+  auto dYl = [&](int l) { return D(6 + 4 * (7 - l)); };       // output of backward step 8 - l
+  int n = 0;
+  // pts_linears.l, heaviest first so the equal-cost cut starts on full-width products
+  for (int l = 1; l < 8; ++l) {
+    const int ld = (l == 5) ? W_ + CH_PTS : W_;
+    need[n] = (signed char)(10 - l);
+    jobs[n++] = WgradJob{dYl(l), dp, A(4 * (l - 1)), ap, grad + pl.w_pts[l], grad + pl.b_pts[l], 4, 4, 4, ld, l == 5 ? CH_PTS : 0, W_, 0, W_};
+  }
+  need[n] = 2; jobs[n++] = WgradJob{D(2), dp, A(28), ap, grad + pl.w_feat, grad + pl.b_feat, 4, 4, 4, W_, 0, W_, 0, W_};                       // feature_linear
+  need[n] = 1; jobs[n++] = WgradJob{D(0), dp, A(tr::IMG_FEAT), ap, grad + pl.w_views, grad + pl.b_views, 2, 2, 4, W_ + CH_DIR, 0, W_, 0, 128};    // views_linears.0 [:, :256]
+  need[n] = 1; jobs[n++] = WgradJob{D(tr::IMG_DY_HEAD), dp, A(28), ap, grad + pl.w_alpha, grad + pl.b_alpha, 2, 1, 4, W_, 0, W_, 3, 4};           // alpha_linear (head row 3)
+  need[n] = 1; jobs[n++] = WgradJob{D(tr::IMG_DY_HEAD), dp, A(tr::IMG_HV), ap, grad + pl.w_rgb, grad + pl.b_rgb, 2, 1, 2, 128, 0, 128, 0, 3};     // rgb_linear (head rows 0..2)
+  need[n] = 10; jobs[n++] = WgradJob{dYl(0), dp, A(tr::IMG_PE), ap, grad + pl.w_pts[0], grad + pl.b_pts[0], 4, 4, 1, CH_PTS, 0, CH_PTS, 0, W_};   // pts_linears.0
+  need[n] = 5; jobs[n++] = WgradJob{dYl(5), dp, A(tr::IMG_PE), ap, grad + pl.w_pts[5], nullptr, 4, 4, 1, W_ + CH_PTS, 0, CH_PTS, 0, W_};          // pts_linears.5 [:, :63] (skip input)
+  need[n] = 1; jobs[n++] = WgradJob{D(0), dp, A(tr::IMG_DIR), ap, grad + pl.w_views, nullptr, 2, 2, 1, W_ + CH_DIR, W_, CH_DIR, 0, 128};          // views_linears.0 [:, 256:]
+  return n;
+}
+
 // Weight gradients of one network from the saved images: 16 products dW = dY^T X (+ bias sums) in ONE grouped tensor-core
 // launch, accumulated into grad [n_params] in state_dict order (the caller zeroes it once per step).
 int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_img, int64_t ntiles, float* grad, void* stream) {
   NFB_REQUIRE(h && act_img && dy_img && grad, "mlp_bwd_weights: null pointer");
   NFB_REQUIRE(ntiles >= 0, "mlp_bwd_weights: ntiles=%lld", (long long)ntiles);
   if (ntiles == 0) return NFB_OK;
-  using namespace nfb;
-  const ParamLayout pl = param_layout();
-  const int64_t ap = (int64_t)tr::FWD_CHUNKS * CHUNK_BYTES, dp = (int64_t)tr::BWD_CHUNKS * CHUNK_BYTES;
-  auto A = [&](int chunk) { return (const void*)((const char*)act_img + (int64_t)chunk * CHUNK_BYTES); };
-  auto D = [&](int chunk) { return (const void*)((const char*)dy_img + (int64_t)chunk * CHUNK_BYTES); };
-  auto dYl = [&](int l) { return D(6 + 4 * (7 - l)); };
-  WgradJob jobs[16];
-  int n = 0;
-  // pts_linears.l, heaviest first so the equal-cost cut starts on full-width products
-  for (int l = 1; l < 8; ++l) {
-    const int ld = (l == 5) ? W_ + CH_PTS : W_;
-    jobs[n++] = WgradJob{dYl(l), dp, A(4 * (l - 1)), ap, grad + pl.w_pts[l], grad + pl.b_pts[l], 4, 4, 4, ld, l == 5 ? CH_PTS : 0, W_, 0, W_};
+  nfb::WgradJob jobs[16];
+  signed char need[16];
+  const int n = wgrad_jobs(act_img, dy_img, grad, jobs, need);
+  return nfb::launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, stream, "mlp_bwd_weights");
+}
+
+// Whole backward of one network: the data-gradient chain and the grouped weight-gradient kernel run CONCURRENTLY on
+// disjoint SMs (producer clusters on `stream`, consumer CTAs on the handle's side stream, fork / join by events).  The
+// producer publishes per tile how many of its dY store groups have landed (ready [tiles] int32, zeroed here); a consumer
+// CTA loads a tile's dY as soon as its product's chunks are complete, i.e. out of L2 while the lines are still resident,
+// so the 5 KB / sample of dY is written to HBM once and never read back from it.  Results are identical to
+// nfb_mlp_bwd_data followed by nfb_mlp_bwd_weights up to the order of the fp32 reductions.
+// NERFAIL_B200_BWD_PRODUCERS = number of producer CTA pairs (default 40 of 74); batches smaller than that run serially.
+int nfb_mlp_bwd(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_t* mask, const void* act_img,
+                void* dy_img, float* grad, int* ready, void* stream) {
+  NFB_REQUIRE(h && g_raw && mask && act_img && dy_img && grad && ready, "mlp_bwd: null pointer");
+  NFB_REQUIRE(M >= 0, "mlp_bwd: M=%lld", (long long)M);
+  if (M == 0) return NFB_OK;
+  static const int env_groups = []() { const char* e = getenv("NERFAIL_B200_BWD_PRODUCERS"); return e ? atoi(e) : 40; }();
+  const int64_t ntiles = nfb_mlp_train_tiles(M);
+  const int pairs = nfb::sm_count() / 2;
+  int groups = env_groups;
+  const int consumers = 2 * (pairs - groups);
+  if (groups <= 0 || consumers < 16 || ntiles / 4 < groups || ntiles >= 32768) {
+    int rc = nfb_mlp_bwd_data(h, g_raw, M, mask, dy_img, stream);
+    if (rc != NFB_OK) return rc;
+    return nfb_mlp_bwd_weights(h, act_img, dy_img, ntiles, grad, stream);
   }
-  jobs[n++] = WgradJob{D(2), dp, A(28), ap, grad + pl.w_feat, grad + pl.b_feat, 4, 4, 4, W_, 0, W_, 0, W_};                       // feature_linear
-  jobs[n++] = WgradJob{D(0), dp, A(tr::IMG_FEAT), ap, grad + pl.w_views, grad + pl.b_views, 2, 2, 4, W_ + CH_DIR, 0, W_, 0, 128};    // views_linears.0 [:, :256]
-  jobs[n++] = WgradJob{D(tr::IMG_DY_HEAD), dp, A(28), ap, grad + pl.w_alpha, grad + pl.b_alpha, 2, 1, 4, W_, 0, W_, 3, 4};           // alpha_linear (head row 3)
-  jobs[n++] = WgradJob{D(tr::IMG_DY_HEAD), dp, A(tr::IMG_HV), ap, grad + pl.w_rgb, grad + pl.b_rgb, 2, 1, 2, 128, 0, 128, 0, 3};     // rgb_linear (head rows 0..2)
-  jobs[n++] = WgradJob{dYl(0), dp, A(tr::IMG_PE), ap, grad + pl.w_pts[0], grad + pl.b_pts[0], 4, 4, 1, CH_PTS, 0, CH_PTS, 0, W_};    // pts_linears.0
-  jobs[n++] = WgradJob{dYl(5), dp, A(tr::IMG_PE), ap, grad + pl.w_pts[5], nullptr, 4, 4, 1, W_ + CH_PTS, 0, CH_PTS, 0, W_};          // pts_linears.5 [:, :63] (skip input)
-  jobs[n++] = WgradJob{D(0), dp, A(tr::IMG_DIR), ap, grad + pl.w_views, nullptr, 2, 2, 1, W_ + CH_DIR, W_, CH_DIR, 0, 128};          // views_linears.0 [:, 256:]
-  return launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, stream, "mlp_bwd_weights");
+  cudaStream_t main_s = (cudaStream_t)stream;
+  // profiling only (NERFAIL_B200_BWD_MODE): 1 = producer alone on its CTA pairs, 2 = consumer alone on its CTAs (ready left
+  // at 10 by an earlier call), 3 = both, one after the other on `stream`
+  static const int dbg_mode = []() { const char* e = getenv("NERFAIL_B200_BWD_MODE"); return e ? atoi(e) : 0; }();
+  cudaStream_t cons_s = (dbg_mode == 0) ? h->side_stream : main_s;
+  if (dbg_mode != 2) NFB_CUDA(cudaMemsetAsync(ready, 0, sizeof(int) * ntiles, main_s));
+  if (dbg_mode == 0) {
+    NFB_CUDA(cudaEventRecord(h->ev_fork, main_s));
+    NFB_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+  }
+  nfb::tr::TrainArgs a{};
+  a.image = h->image_t; a.side = h->side; a.cslot = h->cslot; a.abort_flag = h->abort_flag;
+  a.M = M; a.S = 1; a.g_raw = g_raw; a.mask = const_cast<uint32_t*>(mask); a.dy_img = (char*)dy_img; a.ready = ready;
+  int rc = (dbg_mode == 2) ? NFB_OK : train_launch(nfb::tr::MODE_BWD, h, a, stream, groups);
+  nfb::WgradJob jobs[16];
+  signed char need[16];
+  const int n = wgrad_jobs(act_img, dy_img, grad, jobs, need);
+  if (rc == NFB_OK && dbg_mode != 1)
+    rc = nfb::launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, cons_s, "mlp_bwd", ready, need, consumers);
+  if (dbg_mode != 0) return rc;
+  // join even after a failed launch so the caller's stream never runs ahead of the side stream
+  cudaEventRecord(h->ev_join, h->side_stream);
+  cudaStreamWaitEvent(main_s, h->ev_join, 0);
+  return rc;
 }
 
 // Profiling aid: full forward with a timeline of CTA 0 written to trace [3][2048][4] uint64 (see FwdArgs::trace).

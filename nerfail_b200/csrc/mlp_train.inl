@@ -44,6 +44,9 @@ struct TrainArgs {
   const float* g_raw;             // [M,4] in         (MODE_BWD)
   char* act_img;                  // [ntiles][40][16 KB]  written by MODE_FWD
   uint32_t* mask;                 // [ntiles][9][8][128]  written by MODE_FWD, read by MODE_BWD
+  int* ready;                     // [ntiles] or null (MODE_BWD): published count of landed store groups per tile, for a
+                                  // concurrently running wgrad_kernel in consumer mode: 1 = dY_views + head chunk,
+                                  // 1 + b = output of backward step b - 1 as well (10 = everything)
   int skip;                       // profiling only (NERFAIL_B200_TRAIN_SKIP): bit 0 = no mask stores, bit 1 = no image stores
   char* dy_img;                   // [ntiles][39][16 KB]  written by MODE_BWD
 };
@@ -81,6 +84,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_but_last() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all_but_two() { asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); }
+// the bulk stores counted so far have landed (wait_group without .read): make them visible device-wide, then publish
+__device__ __forceinline__ void publish_ready(int* p, int count) {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  __threadfence();
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(count) : "memory");
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -249,6 +259,7 @@ mlp_train_kernel(const TrainArgs a) {
     bias_s[tslot] = bias_elem(0);
     slot_sync();
 
+    int64_t prev_tile = -1;
     for (int64_t unit = group; unit < nunits; unit += ngroups) {
       const int64_t m = unit * ROWS_PER_UNIT + (int64_t)g * (TILE_M * CG) + rank * TILE_M + row;
       const int64_t tile = (unit * 2 + g) * CG + rank;          // = m / 128
@@ -331,6 +342,12 @@ mlp_train_kernel(const TrainArgs a) {
         // stores are HBM-bound (64 KB per slot and step), so this doubles the time they have before they stall the drain.
         const bool wait_all = (MODE == MODE_BWD && s == 0) || (MODE == MODE_FWD && s == 9);   // previous group read chunks 0/1
         if (tslot == 0) { if (wait_all) bulk_wait_read(); else bulk_wait_read_but_last(); }
+        if (MODE == MODE_BWD && a.ready && tslot == 0 && s >= 1) {
+          // committed so far: the input-stage group and two groups per finished step; all but the last two have landed
+          bulk_wait_all_but_two();
+          publish_ready(a.ready + tile, s);
+          if (s == 1 && prev_tile >= 0) publish_ready(a.ready + prev_tile, 1 + BWD_STEPS);
+        }
         slot_sync();
 
         if (MODE == MODE_FWD && s == 9) {
@@ -501,8 +518,12 @@ mlp_train_kernel(const TrainArgs a) {
         slot_sync();
         if (!last) signal_a_ready();
       }
+      prev_tile = tile;
     }
-    if (tslot == 0) bulk_wait_all();                   // the images must be complete in HBM when the kernel ends
+    if (tslot == 0) {
+      bulk_wait_all();                                 // the images must be complete in HBM when the kernel ends
+      if (MODE == MODE_BWD && a.ready && prev_tile >= 0) publish_ready(a.ready + prev_tile, 1 + BWD_STEPS);
+    }
   }
 
   tc_fence_before();

@@ -93,6 +93,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 constexpr int MAX_JOBS = 16;
+constexpr int MAX_CTAS = 160;
 
 // One product dW = dY^T X of a grouped launch.  dY chunks [ndy_real, ndy) are read from a 16 KB block of zeros (pitch 0,
 // L2 resident) so that a product with fewer than 128 output rows still fills an M = 128 MMA.
@@ -111,18 +112,30 @@ struct Args {
   int64_t ntiles;
   const char* zero;                     // 16 KB of zeros (only read when some job has ndy_real < ndy)
   int* flag;
+  // consumer mode (ready != null): the dY image is being written by a concurrently running mlp_train_kernel<BWD>, which
+  // publishes per tile how many of its store groups have landed.  Every CTA then owns ONE job and the tiles
+  // cta_first, cta_first + cta_stride, ... in increasing order (the order the producer finishes them in), and waits for
+  // ready[tile] >= job_need[job] before loading a tile, so dY is consumed out of L2 while it is still resident.
+  const int* ready;
+  short cta_job[MAX_CTAS], cta_first[MAX_CTAS], cta_stride[MAX_CTAS];
+  signed char job_need[MAX_JOBS];
   unsigned long long* dbg;              // profiling only (NERFAIL_B200_WGRAD_DBG=1): per CTA globaltimer at start / end
 };
 
 // Work split: the (job, tile) pairs, jobs in table order, are cut into gridDim.x contiguous ranges of equal HBM cost
 // (cost of a tile of job j = ndy + nx chunks moved into shared memory, zero padding included).  A CTA therefore works on one to three consecutive jobs, keeps a
 // job's whole dW in TMEM while it walks that job's tiles and flushes it once per job.
-struct Segment { int64_t lo, hi; };
+struct Segment { int64_t lo, hi, stride; };
+__device__ __forceinline__ int64_t seg_tiles(const Segment& s) { return s.hi > s.lo ? (s.hi - s.lo + s.stride - 1) / s.stride : 0; }
 __device__ __forceinline__ int ring_stages(int stage_bytes) {
   const int n = RING_BYTES / stage_bytes;
   return n < NSTAGE ? n : NSTAGE;
 }
 __device__ __forceinline__ Segment job_segment(const Args& a, int j, int64_t cost_before, int64_t cost_total) {
+  if (a.ready) {
+    if (a.cta_job[blockIdx.x] != j) return Segment{0, 0, 1};
+    return Segment{a.cta_first[blockIdx.x], a.ntiles, a.cta_stride[blockIdx.x]};
+  }
   const int64_t W = a.ntiles * cost_total;
   const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
   const int64_t base = cost_before * a.ntiles;
@@ -132,7 +145,7 @@ __device__ __forceinline__ Segment job_segment(const Args& a, int j, int64_t cos
     const int64_t t = (w - base + c - 1) / c;
     return t < a.ntiles ? t : a.ntiles;
   };
-  return Segment{cut(w0), cut(w1)};
+  return Segment{cut(w0), cut(w1), 1};
 }
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
@@ -193,7 +206,21 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
         for (int s2 = 0; s2 < NSTAGE; ++s2) mbar_wait(EMPTY_B(s2), ((pmask >> s2) & 1u) ^ 1u, flag);
       first = false;
       int st = 0;
-      for (int64_t tile = sg.lo; tile < sg.hi; ++tile) {
+      for (int64_t tile = sg.lo; tile < sg.hi; tile += sg.stride) {
+        if (a.ready) {                                   // wait until the producer kernel has published this tile's dY
+          if (lane == 0) {
+            const int need = a.job_need[j];
+            int v, spins = 0;
+            while (true) {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.ready + tile) : "memory");
+              if (v >= need) break;
+              __nanosleep(200);
+              if ((++spins & 1023) == 0 && (*flag != 0 || spins > (1 << 22))) { *flag = 1; break; }
+            }
+          }
+          __syncwarp();
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
         for (int half = 0; half < 2; ++half) {
           const uint32_t ph = (pmask >> st) & 1u;
           mbar_wait(EMPTY_B(st), ph ^ 1, flag);
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
         mbar_wait(FREE_B, (seg - 1) & 1, flag);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      const int64_t nst = (sg.hi - sg.lo) * 2;
+      const int64_t nst = seg_tiles(sg) * 2;
       for (int64_t i = 0; i < nst; ++i) {
         mbar_wait(FULL_B(st), (pmask >> st) & 1u, flag);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -278,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
       float acc8[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc8[q] = 0.f;
-      const int64_t nst = (sg.hi - sg.lo) * 2;
+      const int64_t nst = seg_tiles(sg) * 2;
       for (int64_t i = 0; i < nst; ++i) {
         mbar_wait(FULL_B(st), (pmask >> st) & 1u, flag);
         const uint32_t empty = EMPTY_B(st);
@@ -367,7 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
 
 // Launches the grouped weight-gradient kernel (declared in common.cuh; the NeRF job table is built in mlp_fused.cu).
 int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const void* zero16k, int* status, void* stream,
-                         const char* what) {
+                         const char* what, const int* ready, const signed char* job_need, int consumer_ctas) {
   NFB_REQUIRE(jobs && njobs > 0 && njobs <= wg::MAX_JOBS && status, "%s: bad job table", what);
   if (ntiles <= 0) return NFB_OK;
   wg::Args a{};
@@ -387,12 +414,49 @@ int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const 
     cost += s.ndy + s.nx;
   }
   a.njobs = njobs; a.ntiles = ntiles; a.zero = (const char*)zero16k; a.flag = status;
+  a.ready = ready;
   NFB_CUDA(cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
   int64_t grid = sm_count();
   if ((int64_t)njobs * ntiles < grid) grid = (int64_t)njobs * ntiles;
+  if (ready) {
+    // consumer mode: CTAs per job proportional to the job's cost (largest-remainder rounding, at least one each)
+    NFB_REQUIRE(job_need && consumer_ctas >= njobs && consumer_ctas <= wg::MAX_CTAS && consumer_ctas % 2 == 0 && ntiles < 32768,
+                "%s: bad consumer split", what);
+    grid = consumer_ctas;
+    int n[wg::MAX_JOBS], given = 0;
+    double frac[wg::MAX_JOBS];
+    for (int j = 0; j < njobs; ++j) {
+      const double share = (double)grid * (jobs[j].ndy + jobs[j].nx) / (double)cost;
+      n[j] = (int)share < 1 ? 1 : (int)share;
+      frac[j] = share - n[j];
+      given += n[j];
+      a.job_need[j] = job_need[j];
+    }
+    while (given < grid) { int b = 0; for (int j = 1; j < njobs; ++j) if (frac[j] > frac[b]) b = j; ++n[b]; frac[b] -= 1.0; ++given; }
+    while (given > grid) { int b = -1; for (int j = 0; j < njobs; ++j) if (n[j] > 1 && (b < 0 || frac[j] < frac[b])) b = j; --n[b]; frac[b] += 1.0; --given; }
+    int c = 0;
+    for (int j = 0; j < njobs; ++j)
+      for (int k = 0; k < n[j]; ++k, ++c) { a.cta_job[c] = (short)j; a.cta_first[c] = (short)k; a.cta_stride[c] = (short)n[j]; }
+  }
   static const bool dbg = []() { const char* e = getenv("NERFAIL_B200_WGRAD_DBG"); return e && e[0] == '1'; }();
   if (dbg) NFB_CUDA(cudaMalloc(&a.dbg, sizeof(unsigned long long) * 2 * grid));
-  wg::wgrad_kernel<<<(unsigned)grid, wg::THREADS, wg::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  if (ready) {
+    // CTA pairs (clusters of 2, no cluster communication) so that the consumers take whole TPCs: whichever of the two
+    // concurrent kernels is placed first, the producer's 2-CTA clusters still find free SM pairs
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(wg::THREADS);
+    cfg.dynamicSmemBytes = wg::SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, wg::wgrad_kernel, a);
+    if (e != cudaSuccess) return fail(NFB_E_CUDA, "%s: cluster launch: %s", what, cudaGetErrorString(e));
+  } else {
+    wg::wgrad_kernel<<<(unsigned)grid, wg::THREADS, wg::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  }
   if (dbg) {     // per-CTA duration against its first job: shows whether the equal-cost split is equal-time
     std::vector<unsigned long long> t(2 * grid);
     NFB_CUDA(cudaMemcpy(t.data(), a.dbg, sizeof(unsigned long long) * 2 * grid, cudaMemcpyDeviceToHost));

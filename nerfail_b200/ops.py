@@ -6,6 +6,7 @@ and the stream.  Reference citations (file:line, relative to the NeRFail tree) n
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -601,8 +602,15 @@ class FusedMLPTrainFn(torch.autograd.Function):
         dy = torch.empty((T, 39, 128, 64), dtype=torch.bfloat16, device=dev)
         grad = torch.zeros(ctx.n_params, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(lib.nfb_mlp_bwd_data(ctx.fused._h, ptr(g_raw), M, ptr(mask), ptr(dy), stream()), "nfb_mlp_bwd_data")
-            check(lib.nfb_mlp_bwd_weights(ctx.fused._h, ptr(act), ptr(dy), T, ptr(grad), stream()), "nfb_mlp_bwd_weights")
+            if os.environ.get("NERFAIL_B200_BWD", "serial") != "overlap":
+                check(lib.nfb_mlp_bwd_data(ctx.fused._h, ptr(g_raw), M, ptr(mask), ptr(dy), stream()), "nfb_mlp_bwd_data")
+                check(lib.nfb_mlp_bwd_weights(ctx.fused._h, ptr(act), ptr(dy), T, ptr(grad), stream()), "nfb_mlp_bwd_weights")
+            else:
+                # data-gradient and weight-gradient kernels side by side, dY handed over through L2 (nfb_mlp_bwd);
+                # opt-in: measured slower than the serial pair on B200 (profiles/r01_train_bf16.md, "overlapped backward")
+                ready = torch.empty(T, dtype=torch.int32, device=dev)
+                check(lib.nfb_mlp_bwd(ctx.fused._h, ptr(g_raw), M, ptr(mask), ptr(act), ptr(dy), ptr(grad), ptr(ready),
+                                      stream()), "nfb_mlp_bwd")
         # views of the flat gradient in state_dict order (the order FusedMLPTrainFn.apply received the parameters in)
         grads, o = [], 0
         for shp in ctx.shapes:

@@ -31,9 +31,15 @@ runs = {
     "train fwd": lambda: lib.nfb_mlp_fwd_train(fused._h, P(rays), P(z), R, S, P(raw), P(act), P(mask), st()),
     "bwd data": lambda: lib.nfb_mlp_bwd_data(fused._h, P(g_raw), M, P(mask), P(dy), st()),
     "bwd weights": lambda: lib.nfb_mlp_bwd_weights(fused._h, P(act), P(dy), T, P(grad), st()),
+    "bwd overlapped": lambda: lib.nfb_mlp_bwd(fused._h, P(g_raw), M, P(mask), P(act), P(dy), P(grad), P(ready), st()),
 }
-flop = {"inference fwd": 1186816, "train fwd": 1186816, "bwd data": 1115392, "bwd weights": 1186816}
-print(f"skip={os.environ.get('NERFAIL_B200_TRAIN_SKIP', '0')}  M={M}")
+ready = torch.full((T,), 10, dtype=torch.int32, device=dev)
+flop = {"inference fwd": 1186816, "train fwd": 1186816, "bwd data": 1115392, "bwd weights": 1186816,
+        "bwd overlapped": 1115392 + 1186816}
+only = os.environ.get("ONLY")
+if only:
+    runs = {k: v for k, v in runs.items() if k in only.split(",") or k == "train fwd"}
+print(f"skip={os.environ.get('NERFAIL_B200_TRAIN_SKIP', '0')}  producers={os.environ.get('NERFAIL_B200_BWD_PRODUCERS', 'default')}  M={M}")
 for name, fn in runs.items():
     for _ in range(2):
         assert fn() == 0

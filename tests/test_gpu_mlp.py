@@ -311,3 +311,41 @@ def test_fused_train_backward_matches_fp32_autograd(cuda):
         assert rel < lim, (n, rel)
     for n, rel in rel_32.items():
         assert rel < (1e-2 if ("alpha" in n or "rgb" in n) else 0.2), (n, rel)
+
+
+def test_mlp_bwd_overlapped_equals_serial(cuda):
+    """nfb_mlp_bwd (data-gradient and weight-gradient kernels concurrently, dY handed over through per-tile ready
+    counters) against nfb_mlp_bwd_data followed by nfb_mlp_bwd_weights on the same saved images: identical dY image,
+    gradients equal up to the order of the fp32 reductions.  Sized so the concurrent path is taken (>= 40 units)."""
+    from nerfail_b200 import _lib, ops
+    net, rays, z = _train_setup(cuda, R=200, S=192, seed=6)
+    lib = _lib.load()
+    fused = net.fused()
+    R, S = z.shape
+    M = R * S
+    T = int(lib.nfb_mlp_train_tiles(M))
+    assert T // 4 >= 40
+    P = lambda t: t.data_ptr()
+    act = torch.empty((T, 40, 128, 64), dtype=torch.bfloat16, device=cuda)
+    mask = torch.empty((T, 9, 8, 128), dtype=torch.int32, device=cuda)
+    raw = torch.empty((R, S, 4), device=cuda)
+    assert lib.nfb_mlp_fwd_train(fused._h, P(rays), P(z), R, S, P(raw), P(act), P(mask), ops.stream()) == 0
+    g_raw = torch.randn(M, 4, generator=torch.Generator().manual_seed(2)).to(cuda)
+    n = int(lib.nfb_mlp_param_count(fused._h))
+    dy_a = torch.zeros((T, 39, 128, 64), dtype=torch.bfloat16, device=cuda)
+    dy_b = torch.zeros_like(dy_a)
+    grad_a = torch.zeros(n, device=cuda)
+    grad_b = torch.zeros(n, device=cuda)
+    assert lib.nfb_mlp_bwd_data(fused._h, P(g_raw), M, P(mask), P(dy_a), ops.stream()) == 0
+    assert lib.nfb_mlp_bwd_weights(fused._h, P(act), P(dy_a), T, P(grad_a), ops.stream()) == 0
+    ready = torch.empty(T, dtype=torch.int32, device=cuda)
+    for rep in range(3):                                   # repeated: a race on the ready counters would not be stable
+        grad_b.zero_()
+        dy_b.zero_()
+        assert lib.nfb_mlp_bwd(fused._h, P(g_raw), M, P(mask), P(act), P(dy_b), P(grad_b), P(ready), ops.stream()) == 0
+        torch.cuda.synchronize()
+        fused.status()
+        assert int(ready.min()) == 10 and int(ready.max()) == 10
+        assert torch.equal(dy_a.view(torch.int16), dy_b.view(torch.int16))
+        scale = float(grad_a.abs().max())
+        assert float((grad_a - grad_b).abs().max()) < 1e-4 * scale, rep
