@@ -319,6 +319,30 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
                            "identical_to_brute_force": bool(torch.equal(i_g, i_b) and torch.equal(d_g, d_b)),
                            "pruning_factor": pairs / max(evals, 1.0), "brute_force_pairs_per_s": pairs / (ms_brute / 1e3),
                            "speedup": ms_brute / ms_grid}
+
+    # ---- novel-view sweep through render_path (nerf_render_only.py:619-648): PNG + host arrays, asynchronous sink ----
+    import shutil
+    import tempfile
+    n_sweep = 6
+    ring = [torch.tensor(p_, dtype=torch.float32) for p_ in synth.camera_ring(n_sweep * world)]
+    tmp = tempfile.mkdtemp(prefix="nfb_sweep_")
+    try:
+        kws = {k: v for k, v in kw.items()}
+        kws.update(near=2.0, far=6.0)
+        with torch.no_grad():
+            nb.render_sweep(ring[:world], (H, W, K[0][0]), K, 1024, kws, savedir=tmp, rank=rank, world_size=world)   # warm-up
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nb.render_sweep(ring, (H, W, K[0][0]), K, 1024, kws, savedir=tmp, rank=rank, world_size=world)
+            torch.cuda.synchronize()
+            ms_sweep = sync_max(1e3 * (time.perf_counter() - t0))
+        out["view_sweep"] = {"metric": "novel-view sweep rays/s through render_sweep (views sharded i mod G; rgb/disp to host, PNG files written)",
+                             "value": n_sweep * world * H * W / (ms_sweep / 1e3), "unit": "rays/s", "views": n_sweep * world,
+                             "ms_per_view_per_rank": ms_sweep / n_sweep, "scaling": "weak", "timing": "host wall clock incl. file writes, max over ranks"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     return out
 
 

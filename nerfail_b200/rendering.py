@@ -245,30 +245,118 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
     return ret_list + [ret_dict]
 
 
+class _ViewSink:
+    """Takes finished views off the GPU without stalling the launch loop: device->host copies into a ring of pinned
+    buffers on a side stream, PNG / .npy encoding on a writer thread (cv2 and numpy release the GIL).  The reference
+    does `.cpu().numpy()` + imageio.imwrite inline per view (run_nerf.py:155-169, nerf_to_coord.py:155-173)."""
+
+    def __init__(self, n_views, H, W, with_pts, savedir, device, depth=3):
+        import queue
+        import threading
+        self.savedir, self.with_pts = savedir, with_pts
+        self.rgbs = np.empty((n_views, H, W, 3), np.float32)
+        self.disps = np.empty((n_views, H, W), np.float32)
+        self.pts = np.empty((n_views, H, W, 3), np.float32) if with_pts else None
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [{"rgb": torch.empty((H, W, 3), dtype=torch.float32).pin_memory(),
+                       "disp": torch.empty((H, W), dtype=torch.float32).pin_memory(),
+                       "pts": torch.empty((H, W, 3), dtype=torch.float32).pin_memory() if with_pts else None,
+                       "free": threading.Event()} for _ in range(depth)]
+        for sl in self.slots:
+            sl["free"].set()
+        self.q = queue.Queue()
+        self.err = None
+        self.thread = threading.Thread(target=self._drain, daemon=True)
+        self.thread.start()
+
+    def put(self, k, name, rgb, disp, pts):
+        sl = self.slots[k % len(self.slots)]
+        sl["free"].wait()
+        sl["free"].clear()
+        self.stream.wait_stream(torch.cuda.current_stream(rgb.device))
+        with torch.cuda.stream(self.stream):
+            sl["rgb"].copy_(rgb, non_blocking=True)
+            sl["disp"].copy_(disp, non_blocking=True)
+            if self.with_pts:
+                sl["pts"].copy_(pts, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.q.put((k, name, sl, done, (rgb, disp, pts)))         # the device tensors stay referenced until copied
+
+    def _drain(self):
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            k, name, sl, done, _keep = job
+            try:
+                done.synchronize()
+                self.rgbs[k] = sl["rgb"].numpy()
+                self.disps[k] = sl["disp"].numpy()
+                if self.with_pts:
+                    self.pts[k] = sl["pts"].numpy()
+                sl["free"].set()
+                if self.savedir is not None:
+                    import cv2
+                    cv2.imwrite(os.path.join(self.savedir, name + '.png'), nerf.to8b(self.rgbs[k])[..., ::-1])
+                    if self.with_pts:
+                        np.save(os.path.join(self.savedir, name + '.npy'), self.pts[k])
+            except Exception as e:                                     # surfaced by close()
+                self.err = e
+                sl["free"].set()
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+        if self.err is not None:
+            raise self.err
+
+
 def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0,
-                with_pts_max=False):
-    """run_nerf.py:137-175 / nerf_to_coord.py:138-180: render every pose, optionally saving PNG (+ pts_max .npy)."""
+                with_pts_max=False, view_ids=None):
+    """run_nerf.py:137-175 / nerf_to_coord.py:138-180: render every pose, optionally saving PNG (+ pts_max .npy).
+    The launch loop never waits for the host: finished views leave through _ViewSink.  view_ids names the files when
+    the poses are one rank's shard of a sweep (render_sweep); default 0, 1, ... like the reference."""
     H, W, focal = hwf
     if render_factor != 0:
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
-    rgbs, disps, pts = [], [], []
-    for i, c2w in enumerate(render_poses):
-        t0 = time.time()
-        out = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], with_pts_max=with_pts_max, **render_kwargs)
-        rgbs.append(out[0].cpu().numpy())
-        disps.append(out[1].cpu().numpy())
-        if with_pts_max:
-            pts.append(out[3].cpu().numpy())
-        if savedir is not None:
-            import cv2
-            rgb8 = nerf.to8b(rgbs[-1])
-            cv2.imwrite(os.path.join(savedir, '{:03d}.png'.format(i)), rgb8[..., ::-1])
-            if with_pts_max:
-                np.save(os.path.join(savedir, '{:03d}.npy'.format(i)), pts[-1])
-        if DEBUG:
-            print(i, time.time() - t0)
-    rgbs, disps = np.stack(rgbs, 0), np.stack(disps, 0)
-    return (rgbs, disps, np.stack(pts, 0)) if with_pts_max else (rgbs, disps)
+    n = len(render_poses)
+    ids = list(range(n)) if view_ids is None else list(view_ids)
+    dev = None
+    sink = None
+    try:
+        for k, c2w in enumerate(render_poses):
+            t0 = time.time()
+            out = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], with_pts_max=with_pts_max, **render_kwargs)
+            if sink is None:
+                dev = out[0].device
+                sink = _ViewSink(n, H, W, with_pts_max, savedir, dev)
+            sink.put(k, '{:03d}'.format(ids[k]), out[0], out[1], out[3] if with_pts_max else None)
+            if DEBUG:
+                print(k, time.time() - t0)
+    finally:
+        if sink is not None:
+            sink.close()
+    if sink is None:
+        z = np.zeros((0, H, W, 3), np.float32)
+        return (z, z[..., 0], z) if with_pts_max else (z, z[..., 0])
+    return (sink.rgbs, sink.disps, sink.pts) if with_pts_max else (sink.rgbs, sink.disps)
+
+
+def render_sweep(render_poses, hwf, K, chunk, render_kwargs, savedir=None, with_pts_max=False, rank=None,
+                 world_size=None):
+    """The novel-view sweep of nerf_render_only.py / nerf_to_coord.py (:619-648) sharded by view: rank r renders the
+    poses i with i % world_size == r (views are independent, no collective) and names its files by the global view
+    index, so the ranks of a node fill one directory exactly like the reference's single process.  Returns
+    (view_ids, rgbs, disps[, pts_max]) of this rank."""
+    from . import dist
+    r, w = dist.world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    ids = dist.shard_views(len(render_poses), rank, world_size)
+    out = render_path([render_poses[i] for i in ids], hwf, K, chunk, render_kwargs, savedir=savedir,
+                      with_pts_max=with_pts_max, view_ids=ids)
+    return (ids,) + tuple(out)
 
 
 def create_nerf(args, device=None):

@@ -224,3 +224,32 @@ def nerf_mlp_bf16_emulated(sd: Dict[str, Tensor], pts: Tensor, dirs: Tensor, ret
     rgb = F.linear(hv, sd["rgb_linear.weight"], sd["rgb_linear.bias"])
     out = torch.cat([rgb, sigma], dim=-1)
     return (out, steps) if return_steps else out
+
+
+# ---------------------------------------------------------------------------------------------
+# R:744-773  ray-batch sampling of the no_batching path (the only one NeRFail's configs use)
+# ---------------------------------------------------------------------------------------------
+def sample_ray_batch(images, poses, i_train, H: int, W: int, K, N_rand: int, step: int, precrop_iters: int,
+                     precrop_frac: float, rng=np.random):
+    """A random training image (R:746), all of its rays (H:157-166 via camera_rays), the pixel grid or its centre crop
+    for the first precrop_iters iterations (R:754-766), N_rand distinct pixels (R:768) -> batch_rays [2,N,3],
+    target_s [N,3], img_i, select_coords [N,2]."""
+    img_i = int(rng.choice(np.asarray(i_train)))
+    target = torch.as_tensor(np.asarray(images[img_i]), dtype=torch.float32)
+    pose = torch.as_tensor(np.asarray(poses[img_i]), dtype=torch.float32)[:3, :4]
+    rays = camera_rays(H, W, K, pose, 0.0, 1.0)
+    rays_o, rays_d = rays[:, 0:3].reshape(H, W, 3), rays[:, 3:6].reshape(H, W, 3)
+    if step < precrop_iters:
+        dH = int(H // 2 * precrop_frac)
+        dW = int(W // 2 * precrop_frac)
+        coords = torch.stack(torch.meshgrid(torch.linspace(H // 2 - dH, H // 2 + dH - 1, 2 * dH),
+                                            torch.linspace(W // 2 - dW, W // 2 + dW - 1, 2 * dW), indexing="ij"), -1)
+    else:
+        coords = torch.stack(torch.meshgrid(torch.linspace(0, H - 1, H), torch.linspace(0, W - 1, W), indexing="ij"), -1)
+    coords = torch.reshape(coords, [-1, 2])
+    select_inds = rng.choice(coords.shape[0], size=[N_rand], replace=False)
+    select_coords = coords[select_inds].long()
+    rays_o = rays_o[select_coords[:, 0], select_coords[:, 1]]
+    rays_d = rays_d[select_coords[:, 0], select_coords[:, 1]]
+    target_s = target[select_coords[:, 0], select_coords[:, 1]][..., :3]
+    return torch.stack([rays_o, rays_d], 0), target_s, img_i, select_coords

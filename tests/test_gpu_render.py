@@ -219,3 +219,128 @@ def test_on_device_index_weight_pipeline_and_reference_file_formats(cuda, tmp_pa
     x, x_rgba = net.perturbed(spatial, w_idx, ori)
     x_ref, x_rgba_ref, _ = go.gauss_forward(spatial.cpu(), w_idx.cpu(), ori.cpu(), 32)
     assert torch.allclose(x.cpu(), x_ref, rtol=1e-4, atol=1e-3) and torch.allclose(x_rgba.cpu(), x_rgba_ref, rtol=1e-4, atol=1e-3)
+
+
+def test_render_path_async_sink_and_view_sharded_sweep(cuda, tmp_path):
+    """render_path (run_nerf.py:137-175 / nerf_to_coord.py:138-180): arrays, PNGs (to8b, RGB order) and pts_max .npy
+    files written by the asynchronous sink equal the per-view render() outputs; render_sweep gives rank r the views
+    i = r mod G under the global file names, so two ranks together reproduce the single-process directory."""
+    import cv2
+    import nerfail_b200 as nb
+    _, kw = make_kwargs(cuda)
+    H = W = 20
+    K, focal = synth.intrinsics(H, W)
+    poses = [torch.tensor(p, dtype=torch.float32) for p in synth.camera_ring(5)]
+    kwr = dict(kw, near=2.0, far=6.0)
+    full = tmp_path / "full"
+    full.mkdir()
+    with torch.no_grad():
+        rgbs, disps, pts = nb.render_path(poses, (H, W, focal), K, 256, kwr, savedir=str(full), with_pts_max=True)
+        for i, c2w in enumerate(poses):
+            rgb, disp, acc, pm, _ = nb.render(H, W, K, chunk=256, c2w=c2w[:3, :4], with_pts_max=True, **kwr)
+            assert np.array_equal(rgbs[i], rgb.cpu().numpy()) and np.array_equal(disps[i], disp.cpu().numpy())
+            assert np.array_equal(pts[i], pm.cpu().numpy())
+            png = cv2.imread(str(full / f"{i:03d}.png"), cv2.IMREAD_UNCHANGED)
+            assert np.array_equal(png[..., ::-1], nb.to8b(rgbs[i]))
+            assert np.array_equal(np.load(full / f"{i:03d}.npy"), pts[i])
+        shard = tmp_path / "shard"
+        shard.mkdir()
+        seen = []
+        for r in range(2):
+            ids, rg, dp = nb.render_sweep(poses, (H, W, focal), K, 256, kwr, savedir=str(shard), rank=r, world_size=2)
+            assert ids == list(range(r, 5, 2)) and rg.shape[0] == len(ids)
+            for k, i in enumerate(ids):
+                assert np.array_equal(rg[k], rgbs[i])
+            seen += ids
+        assert sorted(seen) == list(range(5))
+        for i in range(5):
+            assert np.array_equal(cv2.imread(str(shard / f"{i:03d}.png")), cv2.imread(str(full / f"{i:03d}.png")))
+
+
+def test_ray_batch_sampler_matches_reference_sampling(cuda):
+    """train.sample_ray_batch against the oracle restatement of run_nerf.py:744-773 under the same numpy seed: same
+    image, same pixels (precrop window and full frame), same rays / targets; rank shares partition the batch."""
+    import nerfail_b200 as nb
+    H, W, N = 40, 36, 128
+    K, _ = synth.intrinsics(H, W)
+    rng = np.random.default_rng(3)
+    images = rng.random((6, H, W, 4)).astype(np.float32)
+    poses = np.stack(synth.camera_ring(6)).astype(np.float32)
+    i_train = [0, 2, 3, 5]
+    for step, pre in ((0, 500), (700, 500)):
+        ro = np.random.RandomState(11)
+        rays_ref, tgt_ref, img_ref, coords_ref = no.sample_ray_batch(images, poses, i_train, H, W, K, N, step, pre, 0.5, rng=ro)
+        rg = np.random.RandomState(11)
+        rays, tgt, img_i, coords = nb.sample_ray_batch(images, poses, i_train, H, W, K, N, step, pre, 0.5, rng=rg, device=cuda)
+        assert img_i == img_ref and torch.equal(coords.cpu(), coords_ref)
+        assert torch.equal(tgt.cpu(), tgt_ref)
+        assert torch.allclose(rays.cpu(), rays_ref, rtol=0, atol=1e-6)
+        if step < pre:
+            r0, c0, nr, nc = nb.precrop_window(H, W, 0.5)
+            assert int(coords[:, 0].min()) >= r0 and int(coords[:, 0].max()) < r0 + nr
+        parts = []
+        for r in range(3):
+            rg = np.random.RandomState(11)
+            parts.append(nb.sample_ray_batch(torch.from_numpy(images).to(cuda), poses, i_train, H, W, K, N, step, pre, 0.5,
+                                             rng=rg, device=cuda, rank=r, world_size=3)[3])
+        assert torch.equal(torch.cat(parts, 0).cpu(), coords_ref)
+
+
+def test_train_step_adam_lr_decay_and_reference_checkpoint(cuda, tmp_path, fp32_mode):
+    """train.train_step = render(retraw) -> mse(fine) + mse(coarse) -> backward -> Adam -> lr decay (run_nerf.py:776-800)
+    against the same sequence on the oracle's CPU autograd with torch.optim.Adam; the checkpoint (run_nerf.py:808-816)
+    restores step, weights and optimizer state through create_nerf (run_nerf.py:216-233)."""
+    import nerfail_b200 as nb
+    kw_train, _, _, grad_vars, opt = nb.create_nerf(Args(), device=cuda)
+    sd_c = synth.make_non_degenerate(synth.random_state_dict(0), 0)
+    sd_f = synth.make_non_degenerate(synth.random_state_dict(1), 1)
+    kw_train["network_fn"].load_state_dict(sd_c)
+    kw_train["network_fine"].load_state_dict(sd_f)
+    kw = dict(kw_train, near=2.0, far=6.0, perturb=0.0)
+    H = W = 16
+    K, _ = synth.intrinsics(H, W)
+    images = np.random.default_rng(0).random((2, H, W, 3)).astype(np.float32)
+    poses = np.stack(synth.camera_ring(2)).astype(np.float32)
+    # oracle side: functional parameters + torch.optim.Adam on the CPU
+    pc = {k: v.clone().requires_grad_(True) for k, v in sd_c.items()}
+    pf = {k: v.clone().requires_grad_(True) for k, v in sd_f.items()}
+    opt_ref = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4, betas=(0.9, 0.999))
+    losses, losses_ref = [], []
+    for step in range(3):
+        rng = np.random.RandomState(step)
+        rays, tgt, _, _ = nb.sample_ray_batch(images, poses, [0, 1], H, W, K, 64, step, 0, 0.5, rng=rng, device=cuda)
+        out = nb.train_step(rays, tgt, H, W, K, 1024, kw, opt, 5e-4, 250, step)
+        losses.append(float(out["loss"]))
+        rays11 = torch.cat([rays[0], rays[1], torch.full((64, 1), 2.0, device=cuda), torch.full((64, 1), 6.0, device=cuda),
+                            rays[1] / rays[1].norm(dim=-1, keepdim=True)], -1).cpu()
+        ret = no.render_ray_batch(rays11, pc, pf, white_bkgd=True)
+        loss_ref = ((ret["rgb_map"] - tgt.cpu()) ** 2).mean() + ((ret["rgb0"] - tgt.cpu()) ** 2).mean()
+        opt_ref.zero_grad()
+        loss_ref.backward()
+        opt_ref.step()
+        for gp in opt_ref.param_groups:
+            gp["lr"] = 5e-4 * 0.1 ** (step / 250000.0)
+        losses_ref.append(float(loss_ref.detach()))
+        assert abs(opt.param_groups[0]["lr"] - opt_ref.param_groups[0]["lr"]) < 1e-12
+    assert np.allclose(losses, losses_ref, rtol=1e-3), (losses, losses_ref)
+    # Adam normalises every element's step to ~lr whatever the gradient's size, so elements whose gradient is rounding
+    # noise may step the other way: compare the parameter UPDATES norm-wise (measured <= 12.5 %,
+    # pts_linears.0.weight: 0.4 % of its elements flip), not element-wise; the loss trajectory above is the tight check
+    for name, p in kw_train["network_fine"].named_parameters():
+        ref, init = pf[name].detach().double(), sd_f[name].double()
+        moved = float((ref - init).norm())
+        assert moved > 0 and float((p.detach().cpu().double() - ref).norm()) < 0.3 * moved, name
+    # checkpoint in the reference's format, reloaded through create_nerf
+    a = Args()
+    a.basedir, a.expname, a.no_reload = str(tmp_path), "exp", False
+    path = nb.save_checkpoint(nb.checkpoint_path(a.basedir, a.expname, 3), 3, kw_train, opt)
+    ck = torch.load(path, map_location="cpu")
+    assert sorted(ck) == ["global_step", "network_fine_state_dict", "network_fn_state_dict", "optimizer_state_dict"]
+    assert list(ck["network_fn_state_dict"]) == list(sd_c)
+    kw2, _, start2, _, opt2 = nb.create_nerf(a, device=cuda)
+    assert start2 == 3
+    for (n1, p1), (n2, p2) in zip(kw_train["network_fn"].named_parameters(), kw2["network_fn"].named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2)
+    s1, s2 = opt.state_dict(), opt2.state_dict()
+    assert s1["param_groups"][0]["lr"] == s2["param_groups"][0]["lr"]
+    assert all(torch.equal(s1["state"][k]["exp_avg"], s2["state"][k]["exp_avg"]) for k in s1["state"])
