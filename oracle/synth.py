@@ -97,3 +97,35 @@ def gauss_inputs(seed: int, P: int = 3, H: int = 64, W: int = 64, B: int = 2, lo
     ori = torch.randint(0, 256, (B, H, W, 4), generator=g).to(torch.uint8)
     ori[..., 3] = (disc * 255).to(torch.uint8)
     return s, dist_idx, ori
+
+
+def write_blender_scene(root: str, H: int = 8, W: int = 8, counts=(3, 2, 4), seed: int = 0, train_dir: str = None):
+    """A tiny nerf_synthetic-style scene on disk for the loader tests: transforms_{train,val,test}.json with
+    `camera_angle_x` and per-frame `file_path` / `transform_matrix` (the fields load_blender.py:37-85 reads), RGBA PNGs
+    with a transparent border.  train_dir (optional) receives a second, different set of train images under the same
+    base names — what `run_nerf.py --train_dir` points at after an attack (load_blender.py:62-63)."""
+    import json
+    import os
+
+    import cv2
+    rng = np.random.default_rng(seed)
+    th = 0
+    for split, n in zip(("train", "val", "test"), counts):
+        os.makedirs(os.path.join(root, split), exist_ok=True)
+        frames = []
+        for i in range(n):
+            img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+            img[0, :, 3] = 0
+            img[:, -1, 3] = 0
+            cv2.imwrite(os.path.join(root, split, f"r_{i}.png"), img[..., [2, 1, 0, 3]])       # cv2 writes BGRA
+            if split == "train" and train_dir is not None:
+                os.makedirs(train_dir, exist_ok=True)
+                att = np.clip(img.astype(np.int32) + rng.integers(-8, 9, img.shape), 0, 255).astype(np.uint8)
+                att[..., 3] = img[..., 3]
+                cv2.imwrite(os.path.join(train_dir, f"r_{i}.png"), att[..., [2, 1, 0, 3]])
+            frames.append({"file_path": f"./{split}/r_{i}", "rotation": 0.1,
+                           "transform_matrix": pose_spherical(-180.0 + 37.0 * th, -30.0, 4.0).tolist()})
+            th += 1
+        with open(os.path.join(root, f"transforms_{split}.json"), "w") as fp:
+            json.dump({"camera_angle_x": 0.6911112070083618, "frames": frames}, fp)
+    return root
