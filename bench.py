@@ -121,7 +121,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 2048
+    n = 8192                                   # ~3.5 s of 16-core CPU work per step: K=5, W=3 stays under a minute
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_rays_per_s(256)
     vals, cores = [], 1
@@ -331,7 +331,7 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
         kws.update(near=2.0, far=6.0)
         with torch.no_grad():
             nb.render_sweep(ring[:world], (H, W, K[0][0]), K, 1024, kws, savedir=tmp, rank=rank, world_size=world)   # warm-up
-            if dist is not None:
+            if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -506,9 +506,10 @@ def main():
         if extra:
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, cores = cpu_reference_rays_per_s(4096)
+            n_cpu = 32768                                         # ~14 s of CPU work on a 16-core host
+            v, dt, cores = cpu_reference_rays_per_s(n_cpu)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": f"4096 random rays of the same view, coarse+fine, chunk 1024, {dt:.1f} s of torch-CPU fp32 (oracle/nerf_oracle.py)"}
+                                    "sample": f"{n_cpu} random rays of the same view, coarse+fine, chunk 1024, {dt:.1f} s of torch-CPU fp32 (oracle/nerf_oracle.py)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
