@@ -222,8 +222,10 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
     K, _ = synth.intrinsics(H, W)
     rays_all = ops.get_ray_batch(H, W, K, torch.tensor(synth.camera_ring(8)[1][:3, :4]), 2.0, 6.0, device=dev)
     sel = torch.from_numpy(np.random.default_rng(0).choice(H * W, N_rand, replace=False)).to(dev)
-    rays_t = rays_all[sel][b:e].contiguous()
-    target = torch.rand(N_rand, 3, generator=torch.Generator().manual_seed(5))[b:e].to(dev)
+    target_all = torch.rand(N_rand, 3, generator=torch.Generator().manual_seed(5))
+    batch = {"rays": rays_all[sel][b:e].contiguous(), "target": target_all[b:e].to(dev)}       # strong: the batch is split over ranks
+    sel_w = torch.from_numpy(np.random.default_rng(100 + rank).choice(H * W, N_rand, replace=False)).to(dev)
+    batch_weak = {"rays": rays_all[sel_w].contiguous(), "target": target_all.to(dev)}            # weak: every rank brings N_rand rays
     kwt = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
     kwt.update(perturb=1.0)
     params_c, params_f = list(kw["network_fn"].parameters()), list(kw["network_fine"].parameters())
@@ -232,8 +234,8 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
         for p_ in params_c + params_f:
             p_.grad = None
         with torch.enable_grad():
-            ret = nb.render_rays(rays_t, retraw=True, **kwt)
-            loss = nb.img2mse(ret["rgb_map"], target) + nb.img2mse(ret["rgb0"], target)
+            ret = nb.render_rays(batch["rays"], retraw=True, **kwt)
+            loss = nb.img2mse(ret["rgb_map"], batch["target"]) + nb.img2mse(ret["rgb0"], batch["target"])
             loss.backward()
         nd.allreduce_grads_(params_c, scale=1.0 / world)
         nd.allreduce_grads_(params_f, scale=1.0 / world)
@@ -258,10 +260,13 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
     opt = nb.Adam(params_c + params_f, lr=5e-4, betas=(0.9, 0.999))      # run_nerf.py:213; fused multi-tensor kernel
     plain_step = train_step
 
+    adam_steps = [0]
+
     def train_step_adam():                                               # run_nerf.py:776-800: backward, step, lr decay
         loss = plain_step()
         opt.step()
-        nb.set_lrate(opt, nb.decayed_lrate(5e-4, 250, int(opt.state[params_c[0]]["step"].item())))
+        adam_steps[0] += 1                                               # host-side global_step: no device sync in the loop
+        nb.set_lrate(opt, nb.decayed_lrate(5e-4, 250, adam_steps[0]))
         return loss
     prev = os.environ.get("NERFAIL_B200_TRAIN")
     os.environ["NERFAIL_B200_TRAIN"] = "bf16"       # fused tensor-core forward (saves activations) + dgrad chain + wgrad GEMMs
@@ -270,7 +275,33 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
         sd0 = [p_.detach().clone() for p_ in params_c + params_f]
         train_step = train_step_adam
         ms16_adam = time_train(5)
+        strong_batch, batch = batch, batch_weak
+        ms16_adam_weak = time_train(5)
+        batch = strong_batch
         train_step = plain_step
+
+        # the same step (render -> loss -> backward -> all-reduce -> fused Adam -> lr decay -> re-pack) as ONE CUDA graph
+        from nerfail_b200 import train as ntrain
+
+        def time_graphed(bt, n_iter):
+            opt_g = nb.Adam(params_c + params_f, lr=5e-4, betas=(0.9, 0.999))
+            br = torch.stack([bt["rays"][:, 0:3], bt["rays"][:, 3:6]], 0).contiguous()
+            kwg = dict(kw, perturb=1.0)
+            stepper = ntrain.GraphedTrainStep(br.shape[1], H, W, K, 32768, kwg, opt_g, 5e-4, 250, near=2.0, far=6.0, device=dev)
+            for i in range(5):                                            # 3 eager warm-up steps, capture, one replay
+                stepper(br, bt["target"], i)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for i in range(n_iter):
+                stepper(br, bt["target"], 5 + i)
+            e1.record()
+            torch.cuda.synchronize()
+            return sync_max(e0.elapsed_time(e1)) / n_iter
+        ms_graph = time_graphed(batch, 20)
+        ms_graph_weak = time_graphed(batch_weak, 20)
         with torch.no_grad():                                            # restore the weights the other measurements use
             for p_, w_ in zip(params_c + params_f, sd0):
                 p_.copy_(w_)
@@ -284,6 +315,12 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
                               "value": N_rand / (ms16 / 1e3), "unit": "rays/s", "ms_per_step": ms16, "rays_per_rank": int(e - b),
                               "dtype": "bf16", "optimizer_step": False, "allreduce_bytes": ar_bytes, "scaling": "strong",
                               "with_fused_adam_and_weight_repack": {"ms_per_step": ms16_adam, "value": N_rand / (ms16_adam / 1e3), "unit": "rays/s"},
+                              "cuda_graph_step_with_adam": {"ms_per_step": ms_graph, "value": N_rand / (ms_graph / 1e3), "unit": "rays/s",
+                                                            "note": "whole optimisation step captured once (train.GraphedTrainStep), 20 replays"},
+                              "cuda_graph_step_with_adam_weak": {"ms_per_step": ms_graph_weak, "rays_per_rank": N_rand, "global_batch": N_rand * world,
+                                                                 "value": N_rand * world / (ms_graph_weak / 1e3), "unit": "rays/s"},
+                              "weak_scaling_with_adam": {"ms_per_step": ms16_adam_weak, "rays_per_rank": N_rand, "global_batch": N_rand * world,
+                                                         "value": N_rand * world / (ms16_adam_weak / 1e3), "unit": "rays/s"},
                               "algorithmic_TFLOPs": flop_step / world / (ms16 / 1e3) / 1e12,
                               "fp32_layer_kernels": {"value": N_rand / (ms32 / 1e3), "unit": "rays/s", "ms_per_step": ms32, "dtype": "f32"}}
     for p_ in params_c + params_f:

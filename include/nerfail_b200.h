@@ -168,6 +168,12 @@ typedef struct nfb_adam_tensor {
 } nfb_adam_tensor;
 NFB_API int nfb_adam_step(const nfb_adam_tensor* tensors, int count, int64_t step, double lr, double beta1, double beta2,
                           double eps, double grad_scale, void* stream);
+/* CUDA-graph form of the same update: the two step-dependent constants (lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step);
+ * nfb_adam_step_scalars computes them on the host exactly as nfb_adam_step does) are read from step_scalars [2] in device
+ * memory when the kernel RUNS, so a captured training step is replayed with the current step and learning rate. */
+NFB_API int nfb_adam_step_scalars(int64_t step, double lr, double beta1, double beta2, float* out2);
+NFB_API int nfb_adam_step_dev(const nfb_adam_tensor* tensors, int count, const float* step_scalars, double beta1,
+                              double beta2, double eps, double grad_scale, void* stream);
 
 /* Alpha compositing. replaces: run_nerf.py:262-305 (raw2outputs) and, when pts_max != NULL,
  * nerf_to_coord.py:418-421 (arg-max-weight point o + d*z[argmax], first maximum wins).

@@ -30,7 +30,10 @@ struct AdamTable {
 
 __global__ void __launch_bounds__(ADAM_THREADS)
 adam_kernel(const __grid_constant__ AdamTable tb, float step_size, float one_minus_beta1, float beta2, float one_minus_beta2,
-            float inv_sqrt_bc2, float eps, float grad_scale) {
+            float inv_sqrt_bc2, float eps, float grad_scale, const float* __restrict__ dyn) {
+  // dyn (device, 2 floats) overrides the two step-dependent constants: a launch captured in a CUDA graph is replayed
+  // with the step size and bias correction of the CURRENT step, written by the host before each replay
+  if (dyn) { step_size = __ldg(dyn); inv_sqrt_bc2 = __ldg(dyn + 1); }
   // locate the tensor of this work item (binary search over <= 64 prefix sums held in the parameter bank)
   int lo = 0, hi = tb.count;
   const int item = blockIdx.x;
@@ -60,14 +63,18 @@ adam_kernel(const __grid_constant__ AdamTable tb, float step_size, float one_min
 
 extern "C" {
 
-int nfb_adam_step(const nfb_adam_tensor* tensors, int count, int64_t step, double lr, double beta1, double beta2, double eps,
-                  double grad_scale, void* stream) {
-  NFB_REQUIRE(tensors || count == 0, "adam_step: null tensor table");
-  NFB_REQUIRE(count >= 0 && step >= 1, "adam_step: count=%d step=%lld", count, (long long)step);
-  NFB_REQUIRE(beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0., "adam_step: bad hyper-parameters");
-  // hyper-parameters are Python scalars (doubles) in torch.optim.Adam: derive every constant in double, round once
+// the two step-dependent constants of the update, derived in double like torch's Python scalars and rounded once
+int nfb_adam_step_scalars(int64_t step, double lr, double beta1, double beta2, float* out2) {
+  NFB_REQUIRE(out2 && step >= 1, "adam_step_scalars: step=%lld", (long long)step);
+  NFB_REQUIRE(beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1., "adam_step_scalars: bad betas");
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-  const float step_size = (float)(lr / bc1), inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  out2[0] = (float)(lr / bc1);
+  out2[1] = (float)(1.0 / sqrt(bc2));
+  return NFB_OK;
+}
+
+static int adam_launch(const nfb_adam_tensor* tensors, int count, float step_size, float inv_sqrt_bc2, const float* dyn,
+                       double beta1, double beta2, double eps, double grad_scale, void* stream) {
   for (int t0 = 0; t0 < count; t0 += nfb::ADAM_MAX_TENSORS) {
     nfb::AdamTable tb{};
     const int n = count - t0 < nfb::ADAM_MAX_TENSORS ? count - t0 : nfb::ADAM_MAX_TENSORS;
@@ -83,11 +90,32 @@ int nfb_adam_step(const nfb_adam_tensor* tensors, int count, int64_t step, doubl
     tb.count = n;
     if (items == 0) continue;
     nfb::adam_kernel<<<items, nfb::ADAM_THREADS, 0, (cudaStream_t)stream>>>(tb, step_size, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
-                                                                                  inv_sqrt_bc2, (float)eps, (float)grad_scale);
+                                                                                  inv_sqrt_bc2, (float)eps, (float)grad_scale, dyn);
     int rc = nfb::check_launch("adam_step");
     if (rc) return rc;
   }
   return NFB_OK;
+}
+
+int nfb_adam_step(const nfb_adam_tensor* tensors, int count, int64_t step, double lr, double beta1, double beta2, double eps,
+                  double grad_scale, void* stream) {
+  NFB_REQUIRE(tensors || count == 0, "adam_step: null tensor table");
+  NFB_REQUIRE(count >= 0 && step >= 1, "adam_step: count=%d step=%lld", count, (long long)step);
+  NFB_REQUIRE(beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0., "adam_step: bad hyper-parameters");
+  float sc[2];
+  int rc = nfb_adam_step_scalars(step, lr, beta1, beta2, sc);
+  if (rc) return rc;
+  return adam_launch(tensors, count, sc[0], sc[1], nullptr, beta1, beta2, eps, grad_scale, stream);
+}
+
+// Same update with the step-dependent constants read from device memory (step_scalars = what nfb_adam_step_scalars
+// returns, copied to the device by the caller before the launch runs): the form that can be captured in a CUDA graph.
+int nfb_adam_step_dev(const nfb_adam_tensor* tensors, int count, const float* step_scalars, double beta1, double beta2,
+                      double eps, double grad_scale, void* stream) {
+  NFB_REQUIRE(tensors || count == 0, "adam_step_dev: null tensor table");
+  NFB_REQUIRE(count >= 0 && step_scalars, "adam_step_dev: count=%d", count);
+  NFB_REQUIRE(beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0., "adam_step_dev: bad hyper-parameters");
+  return adam_launch(tensors, count, 0.f, 0.f, step_scalars, beta1, beta2, eps, grad_scale, stream);
 }
 
 }  // extern "C"

@@ -40,13 +40,29 @@ def allreduce_sum_(t: torch.Tensor, async_op: bool = False):
     return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)
 
 
+def _flat_view(grads):
+    """The gradients as ONE tensor without a copy, if they are back-to-back views of one buffer (what the fused training
+    backward hands to autograd: nfb_mlp_bwd_weights accumulates into a flat [n_params] gradient in state_dict order)."""
+    g0 = grads[0]
+    base, off = g0.untyped_storage().data_ptr(), g0.storage_offset()
+    for g in grads:
+        if g.untyped_storage().data_ptr() != base or g.dtype != g0.dtype or not g.is_contiguous() or g.storage_offset() != off:
+            return None
+        off += g.numel()
+    return torch.as_strided(g0, (off - g0.storage_offset(),), (1,), g0.storage_offset())
+
+
 def allreduce_grads_(params: Iterable[torch.nn.Parameter], scale: float = 1.0, async_op: bool = False):
-    """One flat bucket per call (4.77 MB for both NeRF networks): flatten grads, all-reduce, scale, scatter back.
+    """One flat bucket per call (4.77 MB for both NeRF networks): all-reduce, scale.  Gradients that already live in
+    one flat buffer are reduced in place (no flatten / scatter kernels); otherwise flatten, all-reduce, scatter back.
     Call once per network so the coarse bucket is in flight while the fine network's wgrad still runs."""
     ps = [p for p in params if p.grad is not None]
     if not ps:
         return None
-    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    flat = _flat_view([p.grad for p in ps])
+    in_place = flat is not None
+    if not in_place:
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
     work = allreduce_sum_(flat, async_op=async_op)
 
     def finish():
@@ -54,6 +70,8 @@ def allreduce_grads_(params: Iterable[torch.nn.Parameter], scale: float = 1.0, a
             work.wait()
         if scale != 1.0:
             flat.mul_(scale)
+        if in_place:
+            return
         off = 0
         for p in ps:
             n = p.grad.numel()

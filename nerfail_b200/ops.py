@@ -6,6 +6,7 @@ and the stream.  Reference citations (file:line, relative to the NeRFail tree) n
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from typing import Optional
 
@@ -588,7 +589,7 @@ class FusedMLPTrainFn(torch.autograd.Function):
                   "nfb_mlp_fwd_train")
         ctx.fused, ctx.M, ctx.T = fused, M, T
         ctx.shapes = [tuple(p.shape) for p in params]
-        ctx.n_params = sum(int(np.prod(sh)) for sh in ctx.shapes)
+        ctx.n_params = sum(math.prod(sh) for sh in ctx.shapes)
         ctx.save_for_backward(act, mask)
         return raw
 
@@ -614,7 +615,7 @@ class FusedMLPTrainFn(torch.autograd.Function):
         # views of the flat gradient in state_dict order (the order FusedMLPTrainFn.apply received the parameters in)
         grads, o = [], 0
         for shp in ctx.shapes:
-            n = int(np.prod(shp))
+            n = math.prod(shp)
             grads.append(grad[o:o + n].view(shp))
             o += n
         return (None, None, None, *grads)

@@ -13,6 +13,7 @@ identical fused Adam step.
 """
 from __future__ import annotations
 
+import math
 import os
 from typing import Optional, Sequence, Tuple
 
@@ -68,6 +69,12 @@ def sample_ray_batch(images, poses, i_train: Sequence[int], H: int, W: int, K, N
     return torch.stack([rays_o, rays_d], 0), target_s, img_i, torch.stack([rows, cols], -1)
 
 
+def _psnr(mse):
+    """mse2psnr (run_nerf_helpers.py:10) without its host-side torch.Tensor([10.]) (a pageable host-to-device copy cannot
+    be captured in a CUDA graph)."""
+    return torch.log(mse) * (-10.0 / math.log(10.0))
+
+
 def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwargs_train: dict, optimizer,
                lrate: float, lrate_decay: int, global_step: int, near: Optional[float] = None,
                far: Optional[float] = None) -> dict:
@@ -82,11 +89,11 @@ def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwarg
         optimizer.zero_grad()
         img_loss = nerf.img2mse(rgb, target_s)
         loss = img_loss
-        out = {"psnr": nerf.mse2psnr(img_loss.detach())}
+        out = {"psnr": _psnr(img_loss.detach())}
         if "rgb0" in extras:
             img_loss0 = nerf.img2mse(extras["rgb0"], target_s)
             loss = loss + img_loss0
-            out["psnr0"] = nerf.mse2psnr(img_loss0.detach())
+            out["psnr0"] = _psnr(img_loss0.detach())
         loss.backward()
     _, world_size = nd.world()
     if world_size > 1:
@@ -99,6 +106,66 @@ def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwarg
     set_lrate(optimizer, decayed_lrate(lrate, lrate_decay, global_step))
     out["loss"] = loss.detach()
     return out
+
+
+class GraphedTrainStep:
+    """train_step captured ONCE in a CUDA graph and replayed: the ~60 launches of a step (ray setup, two fused forward
+    passes, compositing, hierarchical sampling, loss, compositing / data-gradient / weight-gradient kernels, gradient
+    all-reduce, fused Adam, weight re-pack) cost one graph launch on the host instead of ~2.6 ms of Python, which is what
+    bounds a data-parallel step once a rank's share of the batch is below ~2000 rays.  Everything that changes from
+    step to step lives in device memory the graph reads: the ray batch and targets (static buffers filled before the
+    replay), the sampler's random numbers (torch's graph-safe Philox state), Adam's step size and bias correction
+    (optim.Adam.begin_step).  Same arithmetic as train_step; checked by test_graphed_train_step_equals_eager."""
+
+    def __init__(self, n_rays: int, H: int, W: int, K, chunk: int, render_kwargs_train: dict, optimizer, lrate: float,
+                 lrate_decay: int, near: Optional[float] = None, far: Optional[float] = None, device=None, warmup: int = 3):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.args = (H, W, K, chunk)
+        self.kw, self.optimizer = render_kwargs_train, optimizer
+        self.lrate, self.lrate_decay, self.near, self.far = lrate, lrate_decay, near, far
+        self.batch_rays = torch.zeros(2, n_rays, 3, device=self.device)
+        self.target_s = torch.zeros(n_rays, 3, device=self.device)
+        self.warmup = warmup
+        self.graph = None
+        self.out = None
+        optimizer.enable_graph_mode(self.device)
+
+    def _nets(self):
+        return [n for n in (self.kw.get("network_fn"), self.kw.get("network_fine")) if n is not None]
+
+    def _eager(self, global_step):
+        H, W, K, chunk = self.args
+        return train_step(self.batch_rays, self.target_s, H, W, K, chunk, self.kw, self.optimizer, self.lrate,
+                          self.lrate_decay, global_step, self.near, self.far)
+
+    def __call__(self, batch_rays, target_s, global_step: int) -> dict:
+        """One step on (batch_rays [2,n,3], target_s [n,3]); returns {'loss', 'psnr', 'psnr0'} (device scalars that the
+        next call overwrites).  The first `warmup` calls run eagerly on a side stream (they are real steps), the next one
+        is captured, every later one is a replay."""
+        self.batch_rays.copy_(batch_rays, non_blocking=True)
+        self.target_s.copy_(target_s, non_blocking=True)
+        self.optimizer.begin_step()
+        if self.graph is not None:
+            self.graph.replay()
+        elif self.warmup > 0:
+            self.warmup -= 1
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self.out = self._eager(global_step)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.out = self._eager(global_step)
+            self.graph = g
+            g.replay()                      # capture does not execute: this replay IS the step
+        # the graph's Adam kernel moved the parameters behind torch's back: force the next non-graph user to re-pack
+        for n in self._nets():
+            n._fused_version = None
+        set_lrate(self.optimizer, decayed_lrate(self.lrate, self.lrate_decay, global_step))
+        return self.out
 
 
 def save_checkpoint(path: str, global_step: int, render_kwargs_train: dict, optimizer) -> str:

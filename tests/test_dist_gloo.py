@@ -46,6 +46,15 @@ def _worker(rank, world, port, out):
         assert torch.allclose(lin.weight.grad, lin2.weight.grad, atol=1e-6)
         fin = nd.allreduce_grads_(lin.parameters(), async_op=True)      # async bucket path
         fin()
+        # gradients that are back-to-back views of one flat buffer (the fused training backward's layout) are reduced
+        # in place: no flatten / scatter, the views see the reduced values
+        flat = torch.arange(24, dtype=torch.float32) * (rank + 1)
+        lin.weight.grad, lin.bias.grad = flat[:21].view(3, 7), flat[21:].view(3)
+        assert nd._flat_view([lin.weight.grad, lin.bias.grad]).data_ptr() == flat.data_ptr()
+        nd.allreduce_grads_(lin.parameters(), scale=0.5)
+        want = torch.arange(24, dtype=torch.float32) * 3 * 0.5
+        assert torch.equal(flat, want) and torch.equal(lin.bias.grad, want[21:])
+        assert nd._flat_view([lin.bias.grad, lin.weight.grad]) is None  # out of order: falls back to flatten + scatter
         out[rank] = True
     finally:
         dist.destroy_process_group()

@@ -344,3 +344,43 @@ def test_train_step_adam_lr_decay_and_reference_checkpoint(cuda, tmp_path, fp32_
     s1, s2 = opt.state_dict(), opt2.state_dict()
     assert s1["param_groups"][0]["lr"] == s2["param_groups"][0]["lr"]
     assert all(torch.equal(s1["state"][k]["exp_avg"], s2["state"][k]["exp_avg"]) for k in s1["state"])
+
+
+def test_graphed_train_step_equals_eager(cuda, monkeypatch):
+    """GraphedTrainStep (whole optimisation step in one CUDA graph: forward, backward, fused Adam with device-side step
+    constants, weight re-pack) against the eager train_step from the same initial state over 6 steps (3 eager warm-up
+    steps + capture + 2 replays): same losses, same parameters up to the fp32 reduction order of the weight gradients."""
+    import nerfail_b200 as nb
+    from nerfail_b200 import train
+    monkeypatch.setenv("NERFAIL_B200_TRAIN", "bf16")
+    H = W = 32
+    K, _ = synth.intrinsics(H, W)
+    images = np.random.default_rng(0).random((2, H, W, 3)).astype(np.float32)
+    poses = np.stack(synth.camera_ring(2)).astype(np.float32)
+    runs = []
+    for graphed in (False, True):
+        kw_train, _, _, _, opt = nb.create_nerf(Args(), device=cuda)
+        kw_train["network_fn"].load_state_dict(synth.make_non_degenerate(synth.random_state_dict(0), 0))
+        kw_train["network_fine"].load_state_dict(synth.make_non_degenerate(synth.random_state_dict(1), 1))
+        kw = dict(kw_train, near=2.0, far=6.0, perturb=0.0)
+        stepper = train.GraphedTrainStep(256, H, W, K, 1024, kw, opt, 5e-4, 250, device=cuda) if graphed else None
+        losses = []
+        for step in range(6):
+            rng = np.random.RandomState(step)
+            rays, tgt, _, _ = nb.sample_ray_batch(images, poses, [0, 1], H, W, K, 256, step, 0, 0.5, rng=rng, device=cuda)
+            out = stepper(rays, tgt, step) if graphed else nb.train_step(rays, tgt, H, W, K, 1024, kw, opt, 5e-4, 250, step)
+            losses.append(float(out["loss"]))
+        if graphed:
+            assert stepper.graph is not None
+        kw_train["network_fn"].fused().status()
+        sd = {k: v.detach().clone() for k, v in kw_train["network_fine"].state_dict().items()}
+        st = opt.state_dict()
+        runs.append((losses, sd, st))
+    (l0, sd0, st0), (l1, sd1, st1) = runs
+    assert np.allclose(l0, l1, rtol=2e-3), (l0, l1)
+    assert st0["param_groups"][0]["lr"] == st1["param_groups"][0]["lr"]
+    assert all(float(st0["state"][k]["step"]) == float(st1["state"][k]["step"]) == 6.0 for k in st0["state"])
+    init = synth.make_non_degenerate(synth.random_state_dict(1), 1)
+    for k in sd0:
+        moved = float((sd0[k].cpu().double() - init[k].double()).norm())
+        assert float((sd0[k].double() - sd1[k].double()).norm()) < 0.3 * moved + 1e-12, k
