@@ -414,7 +414,9 @@ __device__ __forceinline__ uint32_t a_chunk_addr(int s, int c, uint32_t act, uin
 //                      rows of A and HALF of each weight block (N split), so L2->SMEM weight traffic and SMEM operand
 //                      reads per CTA are halved, one MMA covers N = 256, and both tile slots reuse the resident weights.
 // ---------------------------------------------------------------------------------------------------
-template <int CG>
+// AUX = true: the instantiation behind nfb_mlp_fwd_debug / nfb_mlp_fwd_trace (partial runs, activation dumps, timeline);
+// the production instantiation has those branches compiled out of the issue loop and the epilogue.
+template <int CG, bool AUX = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_fused_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -432,9 +434,10 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   volatile int* abort_flag = a.abort_flag;
-  const int nsteps = a.nsteps;
+  const int nsteps = AUX ? a.nsteps : NSTEP;
+  float* const dbg_out = AUX ? a.dbg : nullptr;
   if ((base & 1023u) != 0u && threadIdx.x == 0) *abort_flag = 1;   // misaligned window: results would be garbage
-  const bool tracing = a.trace != nullptr && blockIdx.x == 0;
+  const bool tracing = AUX && a.trace != nullptr && blockIdx.x == 0;
   int trace_n = 0;
   auto trace_evt = [&](int role, unsigned long long tag, unsigned long long t0, unsigned long long t1, unsigned long long aux) {
     if (tracing && lane == 0 && trace_n < TRACE_CAP) {
@@ -723,13 +726,13 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
                 sig_acc = fmaf(fmaxf(h[4 * j + 3], 0.f), w4.w, sig_acc);
               }
             }
-            if (last && a.dbg) {
+            if (AUX && last && dbg_out) {
               if (live) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   float4 o = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
                   if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                  reinterpret_cast<float4*>(a.dbg + m * 256 + col0)[j] = o;
+                  reinterpret_cast<float4*>(dbg_out + m * 256 + col0)[j] = o;
                 }
               }
             } else {
@@ -788,8 +791,8 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
               r0 = fmaf(h0, w0.x, r0); r0 = fmaf(h1, w0.y, r0); r0 = fmaf(h2, w0.z, r0); r0 = fmaf(h3, w0.w, r0);
               r1 = fmaf(h0, w1.x, r1); r1 = fmaf(h1, w1.y, r1); r1 = fmaf(h2, w1.z, r1); r1 = fmaf(h3, w1.w, r1);
               r2 = fmaf(h0, w2.x, r2); r2 = fmaf(h1, w2.y, r2); r2 = fmaf(h2, w2.z, r2); r2 = fmaf(h3, w2.w, r2);
-              if (a.dbg && live) {
-                reinterpret_cast<float4*>(a.dbg + m * 256 + col0)[j] = make_float4(h0, h1, h2, h3);
+              if (AUX && dbg_out && live) {
+                reinterpret_cast<float4*>(dbg_out + m * 256 + col0)[j] = make_float4(h0, h1, h2, h3);
               }
             }
           }
@@ -878,9 +881,13 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e == cudaSuccess)
@@ -957,8 +964,10 @@ static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const floa
   const int64_t nunits = (a.M + rows_per_unit - 1) / rows_per_unit;
   int groups = nfb::sm_count() / cg;
   if (nunits < groups) groups = (int)nunits;
+  const bool aux = dbg != nullptr || trace != nullptr || nsteps != nfb::NSTEP;
   if (cg == 1) {
-    nfb::mlp_fused_fwd_kernel<1><<<groups, nfb::NUM_THREADS, nfb::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    if (aux) nfb::mlp_fused_fwd_kernel<1, true><<<groups, nfb::NUM_THREADS, nfb::SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    else nfb::mlp_fused_fwd_kernel<1, false><<<groups, nfb::NUM_THREADS, nfb::SMEM_BYTES, (cudaStream_t)stream>>>(a);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(groups * 2));
@@ -969,7 +978,8 @@ static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const floa
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, nfb::mlp_fused_fwd_kernel<2>, a);
+    cudaError_t e = aux ? cudaLaunchKernelEx(&cfg, nfb::mlp_fused_fwd_kernel<2, true>, a)
+                        : cudaLaunchKernelEx(&cfg, nfb::mlp_fused_fwd_kernel<2, false>, a);
     if (e != cudaSuccess) return nfb::fail(NFB_E_CUDA, "mlp_fwd: cluster launch: %s", cudaGetErrorString(e));
   }
   return nfb::check_launch("mlp_fwd");
