@@ -889,9 +889,13 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(nfb::mlp_fused_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+    e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+    e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e != cudaSuccess) {
     cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag); cudaFree(h->zero16k);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -1016,9 +1020,12 @@ static int train_launch(int mode, const nfb_mlp_t* h, nfb::tr::TrainArgs& a, voi
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  const bool aux = a.skip != 0 || a.ready != nullptr;
   cudaError_t e = (mode == nfb::tr::MODE_FWD)
-      ? cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD>, a)
-      : cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD>, a);
+      ? (aux ? cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD, true>, a)
+             : cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD, false>, a))
+      : (aux ? cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, true>, a)
+             : cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, false>, a));
   if (e != cudaSuccess) return nfb::fail(NFB_E_CUDA, "mlp_train: cluster launch: %s", cudaGetErrorString(e));
   return nfb::check_launch(mode == nfb::tr::MODE_FWD ? "mlp_fwd_train" : "mlp_bwd_data");
 }

@@ -92,9 +92,13 @@ __device__ __forceinline__ void publish_ready(int* p, int count) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(count) : "memory");
 }
 
-template <int MODE>
+// AUX = true: the instantiation with the profiling switches (TrainArgs::skip) and the ready counters of the overlapped
+// backward (TrainArgs::ready); the production instantiation has both compiled out of the epilogue.
+template <int MODE, bool AUX = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mlp_train_kernel(const TrainArgs a) {
+  const int skip = AUX ? a.skip : 0;
+  int* const ready = AUX ? a.ready : nullptr;
   constexpr int CG = 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -342,11 +346,11 @@ mlp_train_kernel(const TrainArgs a) {
         // stores are HBM-bound (64 KB per slot and step), so this doubles the time they have before they stall the drain.
         const bool wait_all = (MODE == MODE_BWD && s == 0) || (MODE == MODE_FWD && s == 9);   // previous group read chunks 0/1
         if (tslot == 0) { if (wait_all) bulk_wait_read(); else bulk_wait_read_but_last(); }
-        if (MODE == MODE_BWD && a.ready && tslot == 0 && s >= 1) {
+        if (AUX && MODE == MODE_BWD && ready && tslot == 0 && s >= 1) {
           // committed so far: the input-stage group and two groups per finished step; all but the last two have landed
           bulk_wait_all_but_two();
-          publish_ready(a.ready + tile, s);
-          if (s == 1 && prev_tile >= 0) publish_ready(a.ready + prev_tile, 1 + BWD_STEPS);
+          publish_ready(ready + tile, s);
+          if (s == 1 && prev_tile >= 0) publish_ready(ready + prev_tile, 1 + BWD_STEPS);
         }
         slot_sync();
 
@@ -380,7 +384,7 @@ mlp_train_kernel(const TrainArgs a) {
               r1 = fmaf(h[4 * j], w1.x, r1); r1 = fmaf(h[4 * j + 1], w1.y, r1); r1 = fmaf(h[4 * j + 2], w1.z, r1); r1 = fmaf(h[4 * j + 3], w1.w, r1);
               r2 = fmaf(h[4 * j], w2.x, r2); r2 = fmaf(h[4 * j + 1], w2.y, r2); r2 = fmaf(h[4 * j + 2], w2.z, r2); r2 = fmaf(h[4 * j + 3], w2.w, r2);
             }
-            if (!(a.skip & 1)) mask_tile[(64 + hcol * 2 + cc) * 128 + row] = ~mword;
+            if (!(skip & 1)) mask_tile[(64 + hcol * 2 + cc) * 128 + row] = ~mword;
             const uint32_t cb = act + hcol * CHUNK_BYTES;                // view-layer columns hcol*64 .. -> chunk hcol
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -421,7 +425,7 @@ mlp_train_kernel(const TrainArgs a) {
             fence_proxy_async();
             if (tslot == 0) bulk_wait_read();
             slot_sync();                               // chunks 0 and 2 are final; chunks 1 and 3 may be overwritten
-            if (tslot == 0 && !(a.skip & 2)) {
+            if (tslot == 0 && !(skip & 2)) {
               char* dst = (MODE == MODE_FWD) ? act_tile + (int64_t)(s * 4) * CHUNK_BYTES : dy_tile + (int64_t)dy_chunk0(s) * CHUNK_BYTES;
               bulk_s2g(dst, act, CHUNK_BYTES);
               bulk_s2g(dst + 2 * CHUNK_BYTES, act + 2 * CHUNK_BYTES, CHUNK_BYTES);
@@ -459,7 +463,7 @@ mlp_train_kernel(const TrainArgs a) {
               uint32_t mword = 0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) mword = __funnelshift_l(__float_as_uint(h[j]), mword, 1);
-              if (!(a.skip & 1)) mask_tile[(mask_layer * 8 + hcol * 4 + cc) * 128 + row] = ~mword;
+              if (!(skip & 1)) mask_tile[(mask_layer * 8 + hcol * 4 + cc) * 128 + row] = ~mword;
             }
           } else {
             // backward: dX (+ g_sigma * w_alpha for the layer-7 activation), then relu'
@@ -506,7 +510,7 @@ mlp_train_kernel(const TrainArgs a) {
         fence_proxy_async();
         slot_sync();                                   // activation chunks (and the bias row) of this step are final
         if (tslot == 0) {
-          if (!(a.skip & 2)) {
+          if (!(skip & 2)) {
             char* dst = (MODE == MODE_FWD) ? act_tile + (int64_t)(s * 4) * CHUNK_BYTES : dy_tile + (int64_t)dy_chunk0(s) * CHUNK_BYTES;
             bulk_s2g(dst + CHUNK_BYTES, act + CHUNK_BYTES, CHUNK_BYTES);
             bulk_s2g(dst + 3 * CHUNK_BYTES, act + 3 * CHUNK_BYTES, CHUNK_BYTES);
@@ -522,7 +526,7 @@ mlp_train_kernel(const TrainArgs a) {
     }
     if (tslot == 0) {
       bulk_wait_all();                                 // the images must be complete in HBM when the kernel ends
-      if (MODE == MODE_BWD && a.ready && prev_tile >= 0) publish_ready(a.ready + prev_tile, 1 + BWD_STEPS);
+      if (AUX && MODE == MODE_BWD && ready && prev_tile >= 0) publish_ready(ready + prev_tile, 1 + BWD_STEPS);
     }
   }
 
