@@ -103,7 +103,8 @@ NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, co
  * nfb_mlp_bwd_data runs the data-gradient chain from g_raw [M,4] (d loss / d raw) and leaves every layer's dY as a tile
  * image dy_img [tiles][39][16 KB] (chunk 38 = the upstream gradient itself, dY of the two heads).
  * nfb_mlp_bwd_weights computes every weight / bias gradient of the network from the two images in ONE grouped launch
- * (16 products dW = dY^T X, see nfb_wgrad_bf16) and ACCUMULATES them into grad [nfb_mlp_param_count] in state_dict
+ * (14 tensor-core products dW = dY^T X, see nfb_wgrad_bf16; alpha_linear / rgb_linear as fp32 side sums of g_raw against
+ * operands those products load anyway) and ACCUMULATES them into grad [nfb_mlp_param_count] in state_dict
  * order: zero grad once per step.  tiles = nfb_mlp_train_tiles(M).  A barrier time-out is reported by nfb_mlp_status.
  * nfb_mlp_bwd = both of them as two CONCURRENT kernels on disjoint SMs (the loss.backward() of run_nerf.py:791 for one
  * network): the weight-gradient CTAs consume each tile's dY out of L2 as soon as the data-gradient CTAs have published it
@@ -114,8 +115,8 @@ NFB_API int nfb_mlp_fwd_train(const nfb_mlp_t* h, const float* rays, const float
                               void* act_img, uint32_t* mask, void* stream);
 NFB_API int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_t* mask, void* dy_img,
                              void* stream);
-NFB_API int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_img, int64_t ntiles, float* grad,
-                                void* stream);
+NFB_API int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_img, const float* g_raw, int64_t M,
+                                float* grad, void* stream);
 NFB_API int nfb_mlp_bwd(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_t* mask, const void* act_img,
                         void* dy_img, float* grad, int* ready, void* stream);
 

@@ -42,7 +42,7 @@ SIGNATURES = {
     "nfb_linear_bwd_data": (c_int, [c_ptr, c_int, c_ptr, c_int, c_int, c_ptr, c_int, c_i64, c_int, c_int, c_ptr, c_int, c_int, c_ptr]),
     "nfb_linear_bwd_weight": (c_int, [c_ptr, c_int, c_ptr, c_int, c_int, c_ptr, c_int, c_i64, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_ptr]),
     "nfb_linear_bwd_weight_workspace": (c_i64, [c_i64, c_int, c_int]),
-    "nfb_mlp_bwd_weights": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "nfb_mlp_bwd_weights": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "nfb_mlp_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_wgrad_bf16": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "nfb_adam_step": (c_int, [c_ptr, c_int, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_ptr]),

@@ -47,11 +47,21 @@ struct WgradJob {
   float* out_b;
   int ndy, ndy_real, nx;
   int ld, col0, cols_valid, row_begin, row_end;
+  // Optional side product on CUDA cores, riding on the stages this job loads anyway (the two small heads of the network):
+  //   out_side_w[r * side_ld + c] += sum_rows g[row][side_gcol + r] * S[row][c],  out_side_b[r] += sum_rows g[row][side_gcol + r]
+  // for r < side_rows (<= 3), c < side_cols (<= 256); g = the fp32 upstream gradient g_raw [M,4] (launch argument), S = this
+  // job's X chunks (side_x == null) or side_nx (<= 2) extra chunks at side_x loaded next to them.
+  int side_rows = 0, side_gcol = 0, side_cols = 0, side_ld = 0, side_nx = 0;
+  const void* side_x = nullptr;
+  float* out_side_w = nullptr;
+  float* out_side_b = nullptr;
 };
 // ready / job_need / consumer_ctas: consumer mode (see wgrad.cu): dY is produced concurrently by mlp_train_kernel<BWD>, which
 // publishes ready[tile] = number of its store groups that have landed; job j may load a tile once ready[tile] >= job_need[j].
+// g_raw / M: the fp32 upstream gradient [M,4] the side products read (required when a job has side_rows > 0).
 int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const void* zero16k, int* status, void* stream,
-                         const char* what, const int* ready = nullptr, const signed char* job_need = nullptr, int consumer_ctas = 0);
+                         const char* what, const int* ready = nullptr, const signed char* job_need = nullptr, int consumer_ctas = 0,
+                         const float* g_raw = nullptr, int64_t M = 0);
 
 // ---- device ------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;

@@ -1055,7 +1055,7 @@ int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, const ui
   return train_launch(nfb::tr::MODE_BWD, h, a, stream);
 }
 
-// The 16 products dW = dY^T X (+ bias sums) of one network over the saved images, gradient in state_dict order.
+// The products dW = dY^T X (+ bias sums) of one network over the saved images, gradient in state_dict order.
 // need[j] = value of the data-gradient kernel's per-tile ready counter from which job j's dY chunks of that tile are
 // complete (mlp_train.inl: 1 = input stage (view-layer dY + head chunk), b + 2 = output of backward step b).
 static int wgrad_jobs(const void* act_img, const void* dy_img, float* grad, nfb::WgradJob* jobs, signed char* need) {
@@ -1065,33 +1065,48 @@ static int wgrad_jobs(const void* act_img, const void* dy_img, float* grad, nfb:
   auto A = [&](int chunk) { return (const void*)((const char*)act_img + (int64_t)chunk * CHUNK_BYTES); };
   auto D = [&](int chunk) { return (const void*)((const char*)dy_img + (int64_t)chunk * CHUNK_BYTES); };
   auto dYl = [&](int l) { return D(6 + 4 * (7 - l)); };       // output of backward step 8 - l
+  auto job = [&](const void* dy, const void* x, float* gw, float* gb, int ndy, int nx, int ld, int col0, int cols, int rows) {
+    WgradJob j{};
+    j.dy = dy; j.dy_pitch = dp; j.x = x; j.x_pitch = ap; j.out_w = gw; j.out_b = gb;
+    j.ndy = ndy; j.ndy_real = ndy; j.nx = nx; j.ld = ld; j.col0 = col0; j.cols_valid = cols; j.row_begin = 0; j.row_end = rows;
+    return j;
+  };
   int n = 0;
   // pts_linears.l, heaviest first so the equal-cost cut starts on full-width products
   for (int l = 1; l < 8; ++l) {
     const int ld = (l == 5) ? W_ + CH_PTS : W_;
     need[n] = (signed char)(10 - l);
-    jobs[n++] = WgradJob{dYl(l), dp, A(4 * (l - 1)), ap, grad + pl.w_pts[l], grad + pl.b_pts[l], 4, 4, 4, ld, l == 5 ? CH_PTS : 0, W_, 0, W_};
+    jobs[n++] = job(dYl(l), A(4 * (l - 1)), grad + pl.w_pts[l], grad + pl.b_pts[l], 4, 4, ld, l == 5 ? CH_PTS : 0, W_, W_);
   }
-  need[n] = 2; jobs[n++] = WgradJob{D(2), dp, A(28), ap, grad + pl.w_feat, grad + pl.b_feat, 4, 4, 4, W_, 0, W_, 0, W_};                       // feature_linear
-  need[n] = 1; jobs[n++] = WgradJob{D(0), dp, A(tr::IMG_FEAT), ap, grad + pl.w_views, grad + pl.b_views, 2, 2, 4, W_ + CH_DIR, 0, W_, 0, 128};    // views_linears.0 [:, :256]
-  need[n] = 1; jobs[n++] = WgradJob{D(tr::IMG_DY_HEAD), dp, A(28), ap, grad + pl.w_alpha, grad + pl.b_alpha, 2, 1, 4, W_, 0, W_, 3, 4};           // alpha_linear (head row 3)
-  need[n] = 1; jobs[n++] = WgradJob{D(tr::IMG_DY_HEAD), dp, A(tr::IMG_HV), ap, grad + pl.w_rgb, grad + pl.b_rgb, 2, 1, 2, 128, 0, 128, 0, 3};     // rgb_linear (head rows 0..2)
-  need[n] = 10; jobs[n++] = WgradJob{dYl(0), dp, A(tr::IMG_PE), ap, grad + pl.w_pts[0], grad + pl.b_pts[0], 4, 4, 1, CH_PTS, 0, CH_PTS, 0, W_};   // pts_linears.0
-  need[n] = 5; jobs[n++] = WgradJob{dYl(5), dp, A(tr::IMG_PE), ap, grad + pl.w_pts[5], nullptr, 4, 4, 1, W_ + CH_PTS, 0, CH_PTS, 0, W_};          // pts_linears.5 [:, :63] (skip input)
-  need[n] = 1; jobs[n++] = WgradJob{D(0), dp, A(tr::IMG_DIR), ap, grad + pl.w_views, nullptr, 2, 2, 1, W_ + CH_DIR, W_, CH_DIR, 0, 128};          // views_linears.0 [:, 256:]
+  // feature_linear (X = h_7); alpha_linear rides on it as a side product: dW_alpha = sum_rows g_sigma * h_7
+  need[n] = 2; jobs[n] = job(D(2), A(28), grad + pl.w_feat, grad + pl.b_feat, 4, 4, W_, 0, W_, W_);
+  jobs[n].side_rows = 1; jobs[n].side_gcol = 3; jobs[n].side_cols = W_; jobs[n].side_ld = W_;
+  jobs[n].out_side_w = grad + pl.w_alpha; jobs[n].out_side_b = grad + pl.b_alpha;
+  ++n;
+  need[n] = 1; jobs[n++] = job(D(0), A(tr::IMG_FEAT), grad + pl.w_views, grad + pl.b_views, 2, 4, W_ + CH_DIR, 0, W_, 128);             // views_linears.0 [:, :256]
+  need[n] = 10; jobs[n++] = job(dYl(0), A(tr::IMG_PE), grad + pl.w_pts[0], grad + pl.b_pts[0], 4, 1, CH_PTS, 0, CH_PTS, W_);            // pts_linears.0
+  need[n] = 5; jobs[n++] = job(dYl(5), A(tr::IMG_PE), grad + pl.w_pts[5], nullptr, 4, 1, W_ + CH_PTS, 0, CH_PTS, W_);                   // pts_linears.5 [:, :63] (skip input)
+  // views_linears.0 [:, 256:] (X = encoded direction); rgb_linear rides on it: its operand hv is loaded as two extra
+  // slices, dW_rgb = sum_rows g_rgb * hv
+  need[n] = 1; jobs[n] = job(D(0), A(tr::IMG_DIR), grad + pl.w_views, nullptr, 2, 1, W_ + CH_DIR, W_, CH_DIR, 128);
+  jobs[n].side_rows = 3; jobs[n].side_gcol = 0; jobs[n].side_cols = 128; jobs[n].side_ld = 128; jobs[n].side_nx = 2;
+  jobs[n].side_x = A(tr::IMG_HV); jobs[n].out_side_w = grad + pl.w_rgb; jobs[n].out_side_b = grad + pl.b_rgb;
+  ++n;
   return n;
 }
 
-// Weight gradients of one network from the saved images: 16 products dW = dY^T X (+ bias sums) in ONE grouped tensor-core
-// launch, accumulated into grad [n_params] in state_dict order (the caller zeroes it once per step).
-int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_img, int64_t ntiles, float* grad, void* stream) {
-  NFB_REQUIRE(h && act_img && dy_img && grad, "mlp_bwd_weights: null pointer");
-  NFB_REQUIRE(ntiles >= 0, "mlp_bwd_weights: ntiles=%lld", (long long)ntiles);
-  if (ntiles == 0) return NFB_OK;
+// Weight gradients of one network from the saved images: 14 tensor-core products dW = dY^T X (+ bias sums), the two head
+// products as CUDA-core side sums of g_raw [M,4] against operands two of them load anyway, in ONE grouped launch, accumulated into grad [n_params] in state_dict order (the caller zeroes it once per step).
+int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_img, const float* g_raw, int64_t M,
+                        float* grad, void* stream) {
+  NFB_REQUIRE(h && act_img && dy_img && g_raw && grad, "mlp_bwd_weights: null pointer");
+  NFB_REQUIRE(M >= 0, "mlp_bwd_weights: M=%lld", (long long)M);
+  if (M == 0) return NFB_OK;
+  const int64_t ntiles = nfb_mlp_train_tiles(M);
   nfb::WgradJob jobs[16];
   signed char need[16];
   const int n = wgrad_jobs(act_img, dy_img, grad, jobs, need);
-  return nfb::launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, stream, "mlp_bwd_weights");
+  return nfb::launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, stream, "mlp_bwd_weights", nullptr, nullptr, 0, g_raw, M);
 }
 
 // Whole backward of one network: the data-gradient chain and the grouped weight-gradient kernel run CONCURRENTLY on
@@ -1114,7 +1129,7 @@ int nfb_mlp_bwd(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_
   if (groups <= 0 || consumers < 16 || ntiles / 4 < groups || ntiles >= 32768) {
     int rc = nfb_mlp_bwd_data(h, g_raw, M, mask, dy_img, stream);
     if (rc != NFB_OK) return rc;
-    return nfb_mlp_bwd_weights(h, act_img, dy_img, ntiles, grad, stream);
+    return nfb_mlp_bwd_weights(h, act_img, dy_img, g_raw, M, grad, stream);
   }
   cudaStream_t main_s = (cudaStream_t)stream;
   // profiling only (NERFAIL_B200_BWD_MODE): 1 = producer alone on its CTA pairs, 2 = consumer alone on its CTAs (ready left
@@ -1134,7 +1149,7 @@ int nfb_mlp_bwd(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_
   signed char need[16];
   const int n = wgrad_jobs(act_img, dy_img, grad, jobs, need);
   if (rc == NFB_OK && dbg_mode != 1)
-    rc = nfb::launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, cons_s, "mlp_bwd", ready, need, consumers);
+    rc = nfb::launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, cons_s, "mlp_bwd", ready, need, consumers, g_raw, M);
   if (dbg_mode != 0) return rc;
   // join even after a failed launch so the caller's stream never runs ahead of the side stream
   cudaEventRecord(h->ev_join, h->side_stream);

@@ -32,7 +32,10 @@ constexpr int RING_BYTES = 3 * STAGE_BYTES;             // 192 KB ring, cut into
 constexpr int NSTAGE = 8;                               // upper bound (stage of 24 KB: a 2-chunk dY against a 1-chunk X)
 constexpr int SM_BAR = RING_BYTES;
 constexpr int SM_SCRATCH = SM_BAR + 256;                  // 4 epilogue warps x [32][33] floats (transpose for coalesced reductions)
-constexpr int SMEM_BYTES = SM_SCRATCH + 4 * 32 * 33 * 4;
+constexpr int SM_SIDE = SM_SCRATCH + 4 * 32 * 33 * 4;     // [NSTAGE][64 rows][4] fp32: the stage's rows of g_raw (side products)
+constexpr int SIDE_BYTES = ROWS_PER_STAGE * 16;
+constexpr int SMEM_BYTES = SM_SIDE + NSTAGE * SIDE_BYTES;
+static_assert(SM_SIDE % 16 == 0 && SMEM_BYTES <= 232448, "shared memory map");
 constexpr int THREADS = 32 * 10;                        // warp 0 producer, 1 MMA/TMEM, 2-5 epilogue, 6-9 bias sums
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,6 +107,12 @@ struct Job {
   float* out_b;                         // accumulated into out_b[row - row_begin] (column sums of dY), or null
   int ndy, ndy_real, nx;                // 64-column chunks: dY (2 or 4), of which read from HBM, X (1, 2 or 4)
   int ld, col0, cols_valid, row_begin, row_end;
+  // side product (see WgradJob): side_nx extra chunks at side_x (loaded behind the X slices) or the job's own X
+  int side_rows, side_gcol, side_cols, side_ld, side_nx;
+  const char* side_x;
+  float* out_side_w;
+  float* out_side_b;
+  int cost;                             // relative time of one tile of this job (work split): 4 per chunk moved + side sums
 };
 
 struct Args {
@@ -112,6 +121,8 @@ struct Args {
   int64_t ntiles;
   const char* zero;                     // 16 KB of zeros (only read when some job has ndy_real < ndy)
   int* flag;
+  const float* g_raw;                   // [M,4] fp32 upstream gradient (side products), M rows are valid
+  int64_t M;
   // consumer mode (ready != null): the dY image is being written by a concurrently running mlp_train_kernel<BWD>, which
   // publishes per tile how many of its store groups have landed.  Every CTA then owns ONE job and the tiles
   // cta_first, cta_first + cta_stride, ... in increasing order (the order the producer finishes them in), and waits for
@@ -139,7 +150,7 @@ __device__ __forceinline__ Segment job_segment(const Args& a, int j, int64_t cos
   const int64_t W = a.ntiles * cost_total;
   const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
   const int64_t base = cost_before * a.ntiles;
-  const int64_t c = a.job[j].ndy + a.job[j].nx;
+  const int64_t c = a.job[j].cost;
   auto cut = [&](int64_t w) -> int64_t {
     if (w <= base) return 0;
     const int64_t t = (w - base + c - 1) / c;
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   int64_t cost_total = 0;
-  for (int j = 0; j < a.njobs; ++j) cost_total += a.job[j].ndy + a.job[j].nx;
+  for (int j = 0; j < a.njobs; ++j) cost_total += a.job[j].cost;
   if (a.dbg && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -198,9 +209,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
-      cost_before += jb.ndy + jb.nx;
+      cost_before += jb.cost;
       if (sg.hi <= sg.lo) continue;
-      const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
+      const int stage_bytes = (jb.ndy + jb.nx + jb.side_nx) * SLICE_BYTES;
       const int nst = ring_stages(stage_bytes);
       if (!first)                                        // the ring is re-cut: every stage of the previous job must be free
         for (int s2 = 0; s2 < NSTAGE; ++s2) mbar_wait(EMPTY_B(s2), ((pmask >> s2) & 1u) ^ 1u, flag);
@@ -226,10 +237,22 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
           mbar_wait(EMPTY_B(st), ph ^ 1, flag);
           const uint32_t dst = base + st * stage_bytes;
           const uint32_t full = FULL_B(st);
+          const int st_cur = st;
           pmask ^= 1u << st;
           st = (st + 1 == nst) ? 0 : st + 1;
+          // the stage's 64 rows of g_raw (16 B each) for the side product: only the rows below M exist
+          int64_t side_valid = 0;
+          if (jb.side_rows > 0) {
+            side_valid = a.M - (tile * 128 + half * ROWS_PER_STAGE);
+            side_valid = side_valid < 0 ? 0 : (side_valid > ROWS_PER_STAGE ? ROWS_PER_STAGE : side_valid);
+          }
           if (elect_one()) {
-            mbar_arrive_expect_tx(full, stage_bytes);
+            mbar_arrive_expect_tx(full, stage_bytes + (uint32_t)side_valid * 16);
+            if (side_valid > 0)
+              bulk_g2s(base + SM_SIDE + (st_cur) * SIDE_BYTES, a.g_raw + (tile * 128 + half * ROWS_PER_STAGE) * 4, (uint32_t)side_valid * 16, full);
+            for (int c = 0; c < jb.side_nx; ++c)
+              bulk_g2s(dst + (jb.ndy + jb.nx + c) * SLICE_BYTES, jb.side_x + tile * jb.x_pitch + (int64_t)c * 16384 + half * SLICE_BYTES,
+                       SLICE_BYTES, full);
             for (int c = 0; c < jb.ndy; ++c) {
               const char* src = c < jb.ndy_real ? jb.dy + tile * jb.dy_pitch + (int64_t)c * 16384 + half * SLICE_BYTES : a.zero;
               bulk_g2s(dst + c * SLICE_BYTES, src, SLICE_BYTES, full);
@@ -248,9 +271,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
-      cost_before += jb.ndy + jb.nx;
+      cost_before += jb.cost;
       if (sg.hi <= sg.lo) continue;
-      const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
+      const int stage_bytes = (jb.ndy + jb.nx + jb.side_nx) * SLICE_BYTES;
       const int nst_ring = ring_stages(stage_bytes);
       int st = 0;
       const uint32_t idesc = idesc_mn(64 * jb.nx);
@@ -296,15 +319,27 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
-      cost_before += jb.ndy + jb.nx;
+      cost_before += jb.cost;
       if (sg.hi <= sg.lo) continue;
-      const int stage_bytes = (jb.ndy + jb.nx) * SLICE_BYTES;
+      const int stage_bytes = (jb.ndy + jb.nx + jb.side_nx) * SLICE_BYTES;
       const int nst_ring = ring_stages(stage_bytes);
       int st = 0;
       const bool mine = jb.out_b && c < jb.ndy_real;
       float acc8[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc8[q] = 0.f;
+      // side product: a thread owns one 16-byte unit (8 columns) of S and every RG-th row of the stage; the 128 threads
+      // cover side_cols / 8 units x RG row groups (256 columns: 32 x 4, 128 columns: 16 x 8)
+      const bool side = jb.side_rows > 0;
+      const bool three = jb.side_rows == 3;
+      const int side_slice0 = jb.side_nx ? jb.ndy + jb.nx : jb.ndy;       // first slice of S inside the stage
+      const int nunits = side ? jb.side_cols >> 3 : 32;
+      const int uidx = lane & (nunits - 1);
+      const int RG = 4 * (32 / nunits);
+      const int my_rg = c * (32 / nunits) + lane / nunits;
+      float sa[8], sy[8], sz[8], sb0 = 0.f, sb1 = 0.f, sb2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { sa[q] = 0.f; sy[q] = 0.f; sz[q] = 0.f; }
       const int64_t nst = seg_tiles(sg) * 2;
       for (int64_t i = 0; i < nst; ++i) {
         mbar_wait(FULL_B(st), (pmask >> st) & 1u, flag);
@@ -318,6 +353,36 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
             for (int q = 0; q < 4; ++q) {
               acc8[2 * q] += __uint_as_float(w[q] << 16);
               acc8[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+            }
+          }
+        }
+        if (side) {
+          const int64_t tile = sg.lo + (i >> 1) * sg.stride;
+          int64_t valid = a.M - (tile * 128 + (i & 1) * ROWS_PER_STAGE);
+          valid = valid < 0 ? 0 : (valid > ROWS_PER_STAGE ? ROWS_PER_STAGE : valid);
+          const float4* gs = reinterpret_cast<const float4*>(smem + SM_SIDE + st * SIDE_BYTES);
+          const uint8_t* sx = smem + st * stage_bytes + (side_slice0 + (uidx >> 3)) * SLICE_BYTES;
+          const int unit_s = uidx & 7;
+          const int gc = jb.side_gcol;
+          const int nvalid = (int)valid;
+#pragma unroll 2
+          for (int r = my_rg; r < nvalid; r += RG) {
+            const float4 g = gs[r];                                       // same address across the row group: broadcast
+            const uint4 xv = *reinterpret_cast<const uint4*>(sx + r * 128 + (((unit_s ^ (r & 7)) & 7) << 4));
+            // rows = 1: the column side_gcol of g (sigma: 3); rows = 3: columns 0..2 (the rgb logits)
+            const float g0 = three ? g.x : (gc == 3 ? g.w : gc == 2 ? g.z : gc == 1 ? g.y : g.x);
+            const uint32_t w[4] = {xv.x, xv.y, xv.z, xv.w};
+            sb0 += g0;
+            if (three) { sb1 += g.y; sb2 += g.z; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float xl = __uint_as_float(w[q] << 16), xh = __uint_as_float(w[q] & 0xFFFF0000u);
+              sa[2 * q] = fmaf(g0, xl, sa[2 * q]);
+              sa[2 * q + 1] = fmaf(g0, xh, sa[2 * q + 1]);
+              if (three) {
+                sy[2 * q] = fmaf(g.y, xl, sy[2 * q]); sy[2 * q + 1] = fmaf(g.y, xh, sy[2 * q + 1]);
+                sz[2 * q] = fmaf(g.z, xl, sz[2 * q]); sz[2 * q + 1] = fmaf(g.z, xh, sz[2 * q + 1]);
+              }
             }
           }
         }
@@ -340,6 +405,18 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
           }
         }
       }
+      if (side) {                                   // every row group adds its partial sums (once per job and CTA)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = uidx * 8 + q;
+          red_add_f32(jb.out_side_w + col, sa[q]);
+          if (three) { red_add_f32(jb.out_side_w + jb.side_ld + col, sy[q]); red_add_f32(jb.out_side_w + 2 * jb.side_ld + col, sz[q]); }
+        }
+        if (uidx == 0 && jb.out_side_b) {
+          red_add_f32(jb.out_side_b, sb0);
+          if (three) { red_add_f32(jb.out_side_b + 1, sb1); red_add_f32(jb.out_side_b + 2, sb2); }
+        }
+      }
     }
   } else {
     // ================= epilogue: TMEM -> shared-memory transpose -> coalesced L2 reductions into the gradient =========
@@ -350,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
     for (int j = 0; j < a.njobs; ++j) {
       const Job& jb = a.job[j];
       const Segment sg = job_segment(a, j, cost_before, cost_total);
-      cost_before += jb.ndy + jb.nx;
+      cost_before += jb.cost;
       if (sg.hi <= sg.lo) continue;
       mbar_wait(DONE_B, seg & 1, flag);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -394,7 +471,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
 
 // Launches the grouped weight-gradient kernel (declared in common.cuh; the NeRF job table is built in mlp_fused.cu).
 int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const void* zero16k, int* status, void* stream,
-                         const char* what, const int* ready, const signed char* job_need, int consumer_ctas) {
+                         const char* what, const int* ready, const signed char* job_need, int consumer_ctas,
+                         const float* g_raw, int64_t M) {
   NFB_REQUIRE(jobs && njobs > 0 && njobs <= wg::MAX_JOBS && status, "%s: bad job table", what);
   if (ntiles <= 0) return NFB_OK;
   wg::Args a{};
@@ -409,11 +487,26 @@ int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const 
                 (reinterpret_cast<uintptr_t>(s.x) & 15) == 0, "%s: job %d: images must be 16-byte aligned", what, j);
     NFB_REQUIRE(s.cols_valid > 0 && s.cols_valid <= 64 * s.nx && s.row_begin >= 0 && s.row_end <= 64 * s.ndy &&
                 s.row_begin < s.row_end && s.ld >= s.col0 + s.cols_valid, "%s: job %d: bad output window", what, j);
+    if (s.side_rows > 0) {
+      NFB_REQUIRE(g_raw && M > 0 && (reinterpret_cast<uintptr_t>(g_raw) & 15) == 0, "%s: job %d: side product needs g_raw [M,4]", what, j);
+      NFB_REQUIRE((s.side_rows == 1 || (s.side_rows == 3 && s.side_gcol == 0)) && s.side_gcol >= 0 && s.side_gcol < 4 &&
+                  (s.side_cols == 256 || s.side_cols == 128) && s.side_ld >= s.side_cols && s.out_side_w,
+                  "%s: job %d: bad side product", what, j);
+      NFB_REQUIRE(s.side_x ? (s.side_nx >= 1 && s.side_nx <= 2 && s.side_cols <= 64 * s.side_nx &&
+                              (reinterpret_cast<uintptr_t>(s.side_x) & 15) == 0)
+                           : (s.side_nx == 0 && s.side_cols <= 64 * s.nx), "%s: job %d: bad side operand", what, j);
+    } else {
+      NFB_REQUIRE(s.side_nx == 0 && !s.side_x, "%s: job %d: side operand without side rows", what, j);
+    }
     a.job[j] = wg::Job{(const char*)s.dy, s.dy_pitch, (const char*)s.x, s.x_pitch, s.out_w, s.out_b,
-                       s.ndy, s.ndy_real, s.nx, s.ld, s.col0, s.cols_valid, s.row_begin, s.row_end};
-    cost += s.ndy + s.nx;
+                       s.ndy, s.ndy_real, s.nx, s.ld, s.col0, s.cols_valid, s.row_begin, s.row_end,
+                       s.side_rows, s.side_gcol, s.side_cols, s.side_ld, s.side_nx, (const char*)s.side_x, s.out_side_w, s.out_side_b, 0};
+    // measured (B200, 786 k samples): a stage with the 256-column side sum takes 1.25x, with the 3 x 128 one 1.13x
+    a.job[j].cost = 4 * (s.ndy + s.nx + s.side_nx) + (s.side_rows == 1 ? 8 : s.side_rows == 3 ? 3 : 0);
+    cost += a.job[j].cost;
   }
   a.njobs = njobs; a.ntiles = ntiles; a.zero = (const char*)zero16k; a.flag = status;
+  a.g_raw = g_raw; a.M = M;
   a.ready = ready;
   NFB_CUDA(cudaFuncSetAttribute(wg::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
   int64_t grid = sm_count();
@@ -426,7 +519,7 @@ int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const 
     int n[wg::MAX_JOBS], given = 0;
     double frac[wg::MAX_JOBS];
     for (int j = 0; j < njobs; ++j) {
-      const double share = (double)grid * (jobs[j].ndy + jobs[j].nx) / (double)cost;
+      const double share = (double)grid * a.job[j].cost / (double)cost;
       n[j] = (int)share < 1 ? 1 : (int)share;
       frac[j] = share - n[j];
       given += n[j];
@@ -467,7 +560,7 @@ int launch_wgrad_grouped(const WgradJob* jobs, int njobs, int64_t ntiles, const 
     for (int64_t b = 0; b < grid; ++b) {
       const int64_t w0 = W * b / grid;
       int64_t cb = 0; int j0 = 0;
-      for (int j = 0; j < njobs; ++j) { const int64_t c = jobs[j].ndy + jobs[j].nx; if (w0 < (cb + c) * ntiles) { j0 = j; break; } cb += c; }
+      for (int j = 0; j < njobs; ++j) { const int64_t c = a.job[j].cost; if (w0 < (cb + c) * ntiles) { j0 = j; break; } cb += c; }
       fprintf(stderr, "wgrad cta %3lld first job %2d (ndy %d/%d nx %d)  start %8.1f us  end %8.1f us\n", (long long)b, j0, jobs[j0].ndy_real,
               jobs[j0].ndy, jobs[j0].nx, (t[2 * b] - t0) / 1e3, (t[2 * b + 1] - t0) / 1e3);
     }
@@ -486,7 +579,9 @@ extern "C" {
 int nfb_wgrad_bf16(const void* dy, int64_t dy_tile_pitch, int ndy, const void* x, int64_t x_tile_pitch, int nx,
                    int64_t ntiles, float* out_w, int ld, int col0, int cols_valid, int row_begin, int row_end,
                    float* out_b, int* status, void* stream) {
-  nfb::WgradJob j{dy, dy_tile_pitch, x, x_tile_pitch, out_w, out_b, ndy, ndy, nx, ld, col0, cols_valid, row_begin, row_end};
+  nfb::WgradJob j{};
+  j.dy = dy; j.dy_pitch = dy_tile_pitch; j.x = x; j.x_pitch = x_tile_pitch; j.out_w = out_w; j.out_b = out_b;
+  j.ndy = ndy; j.ndy_real = ndy; j.nx = nx; j.ld = ld; j.col0 = col0; j.cols_valid = cols_valid; j.row_begin = row_begin; j.row_end = row_end;
   return nfb::launch_wgrad_grouped(&j, 1, ntiles, nullptr, status, stream, "wgrad_bf16");
 }
 

@@ -605,7 +605,7 @@ class FusedMLPTrainFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             if os.environ.get("NERFAIL_B200_BWD", "serial") != "overlap":
                 check(lib.nfb_mlp_bwd_data(ctx.fused._h, ptr(g_raw), M, ptr(mask), ptr(dy), stream()), "nfb_mlp_bwd_data")
-                check(lib.nfb_mlp_bwd_weights(ctx.fused._h, ptr(act), ptr(dy), T, ptr(grad), stream()), "nfb_mlp_bwd_weights")
+                check(lib.nfb_mlp_bwd_weights(ctx.fused._h, ptr(act), ptr(dy), ptr(g_raw), M, ptr(grad), stream()), "nfb_mlp_bwd_weights")
             else:
                 # data-gradient and weight-gradient kernels side by side, dY handed over through L2 (nfb_mlp_bwd);
                 # opt-in: measured slower than the serial pair on B200 (profiles/r01_train_bf16.md, "overlapped backward")

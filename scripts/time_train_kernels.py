@@ -30,7 +30,7 @@ runs = {
     "inference fwd": lambda: lib.nfb_mlp_fwd(fused._h, 1, None, None, P(rays), P(z), R, S, P(raw), st()),
     "train fwd": lambda: lib.nfb_mlp_fwd_train(fused._h, P(rays), P(z), R, S, P(raw), P(act), P(mask), st()),
     "bwd data": lambda: lib.nfb_mlp_bwd_data(fused._h, P(g_raw), M, P(mask), P(dy), st()),
-    "bwd weights": lambda: lib.nfb_mlp_bwd_weights(fused._h, P(act), P(dy), T, P(grad), st()),
+    "bwd weights": lambda: lib.nfb_mlp_bwd_weights(fused._h, P(act), P(dy), P(g_raw), M, P(grad), st()),
     "bwd overlapped": lambda: lib.nfb_mlp_bwd(fused._h, P(g_raw), M, P(mask), P(act), P(dy), P(grad), P(ready), st()),
 }
 ready = torch.full((T,), 10, dtype=torch.int32, device=dev)

@@ -337,7 +337,7 @@ def test_mlp_bwd_overlapped_equals_serial(cuda):
     grad_a = torch.zeros(n, device=cuda)
     grad_b = torch.zeros(n, device=cuda)
     assert lib.nfb_mlp_bwd_data(fused._h, P(g_raw), M, P(mask), P(dy_a), ops.stream()) == 0
-    assert lib.nfb_mlp_bwd_weights(fused._h, P(act), P(dy_a), T, P(grad_a), ops.stream()) == 0
+    assert lib.nfb_mlp_bwd_weights(fused._h, P(act), P(dy_a), P(g_raw), M, P(grad_a), ops.stream()) == 0
     ready = torch.empty(T, dtype=torch.int32, device=cuda)
     for rep in range(3):                                   # repeated: a race on the ready counters would not be stable
         grad_b.zero_()
