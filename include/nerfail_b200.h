@@ -101,7 +101,7 @@ NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, co
  * nfb_mlp_fwd_train = nfb_mlp_fwd (mode 1) that also leaves, per 128-row tile, every layer's bf16 activation as a tile
  * image act_img [tiles][40][16 KB] and the relu masks as bit words mask [tiles][9][8][128] (layout: csrc/mlp_train.inl).
  * nfb_mlp_bwd_data runs the data-gradient chain from g_raw [M,4] (d loss / d raw) and leaves every layer's dY as a tile
- * image dy_img [tiles][39][16 KB] (chunk 38 = the upstream gradient itself, dY of the two heads).
+ * image dy_img [tiles][39][16 KB] (chunk 38 is reserved and left unwritten).
  * nfb_mlp_bwd_weights computes every weight / bias gradient of the network from the two images in ONE grouped launch
  * (14 tensor-core products dW = dY^T X, see nfb_wgrad_bf16; alpha_linear / rgb_linear as fp32 side sums of g_raw against
  * operands those products load anyway) and ACCUMULATES them into grad [nfb_mlp_param_count] in state_dict

@@ -1057,7 +1057,7 @@ int nfb_mlp_bwd_data(const nfb_mlp_t* h, const float* g_raw, int64_t M, const ui
 
 // The products dW = dY^T X (+ bias sums) of one network over the saved images, gradient in state_dict order.
 // need[j] = value of the data-gradient kernel's per-tile ready counter from which job j's dY chunks of that tile are
-// complete (mlp_train.inl: 1 = input stage (view-layer dY + head chunk), b + 2 = output of backward step b).
+// complete (mlp_train.inl: 1 = input stage (view-layer dY), b + 2 = output of backward step b).
 static int wgrad_jobs(const void* act_img, const void* dy_img, float* grad, nfb::WgradJob* jobs, signed char* need) {
   using namespace nfb;
   const ParamLayout pl = param_layout();

@@ -12,8 +12,8 @@
 // Tile-image chunk indices (16 KB chunks, 128 rows x 64 columns, 128-byte swizzle):
 //   forward  : h_s (s = 0..7) at 4 s .. 4 s + 3, feature at 32..35, view-layer output at 36..37, encoded point 38,
 //              encoded direction 39                                            -> FWD_CHUNKS = 40 per tile
-//   backward : dY_views 0..1, dY_feature 2..5, dY_l (l = 7..0) at 6 + 4 (7 - l), head chunk 38 (columns 0..3 = the upstream
-//              gradient of the rgb logits and of sigma, the rest zero: dY of the two heads) -> BWD_CHUNKS = 39 per tile
+//   backward : dY_views 0..1, dY_feature 2..5, dY_l (l = 7..0) at 6 + 4 (7 - l); chunk 38 is reserved and not written (it
+//              held dY of the two heads before their weight gradients became side sums of g_raw) -> BWD_CHUNKS = 39 per tile
 //   masks    : [tile][9][8 words][128 rows]: words of h_0..h_7 (index 0..7) and of the view layer (index 8, 4 words);
 //              word w of a row covers columns 32 w .. 32 w + 31, column 32 w + j = bit 31 - j (a warp stores / loads
 //              128 contiguous bytes)
@@ -45,7 +45,7 @@ struct TrainArgs {
   char* act_img;                  // [ntiles][40][16 KB]  written by MODE_FWD
   uint32_t* mask;                 // [ntiles][9][8][128]  written by MODE_FWD, read by MODE_BWD
   int* ready;                     // [ntiles] or null (MODE_BWD): published count of landed store groups per tile, for a
-                                  // concurrently running wgrad_kernel in consumer mode: 1 = dY_views + head chunk,
+                                  // concurrently running wgrad_kernel in consumer mode: 1 = dY_views,
                                   // 1 + b = output of backward step b - 1 as well (10 = everything)
   int skip;                       // profiling only (NERFAIL_B200_TRAIN_SKIP): bit 0 = no mask stores, bit 1 = no image stores
   char* dy_img;                   // [ntiles][39][16 KB]  written by MODE_BWD
@@ -316,19 +316,11 @@ mlp_train_kernel(const TrainArgs a) {
           const uint32_t addr = cb + row * 128 + (((u ^ (row & 7)) & 7) << 4);
           st_shared_v4(addr, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         }
-        // head chunk (dY of rgb_linear / alpha_linear for the weight-gradient GEMMs): row = [g_rgb, g_sigma, 0 ...]
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = hcol * 4 + u;
-          const uint32_t addr = pe + row * 128 + (((unit ^ (row & 7)) & 7) << 4);
-          if (unit == 0) st_shared_v4(addr, pack_bf16(gr.x, gr.y), pack_bf16(gr.z, gr.w), 0u, 0u);
-          else st_shared_v4(addr, 0u, 0u, 0u, 0u);
-        }
+        // (the two heads' weight gradients are side sums of g_raw itself in wgrad.cu: no dY chunk is written for them)
         fence_proxy_async();
         slot_sync();
         if (tslot == 0) {
           bulk_s2g(dy_tile, act, 2 * CHUNK_BYTES);
-          bulk_s2g(dy_tile + (int64_t)IMG_DY_HEAD * CHUNK_BYTES, pe, CHUNK_BYTES);
           bulk_commit();
         }
       }
