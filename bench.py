@@ -534,8 +534,8 @@ def main():
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_v3_cta_group2.md (199.5 MB for 12.58 M
                          # samples = 15.86 B/sample; algorithmic 20 B/sample) scaled to this run's average launch
-                         "traffic": 15.86 * (mlp_flop / FLOP_PER_SAMPLE) / max(1, n_mlp_launches),
-                         "traffic_unit": "bytes per launch (ncu --set full, profiles/r01_v3_cta_group2.md)",
+                         "traffic": 15.68 * (mlp_flop / FLOP_PER_SAMPLE) / max(1, n_mlp_launches),
+                         "traffic_unit": "bytes per launch = 15.68 B/sample (dram read + write of one ncu --set full capture, profiles/r01_final.md) x samples per launch",
                          "peak_source": f"{how} bf16_tflops_sustained", "launches": n_mlp_launches,
                          "avg_launch_ms": mlp_ms / max(1, n_mlp_launches),
                          "algorithmic_flop_per_sample": FLOP_PER_SAMPLE, "share_of_step": mlp_ms / ms},
