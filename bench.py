@@ -360,7 +360,7 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
     # ---- novel-view sweep through render_path (nerf_render_only.py:619-648): PNG + host arrays, asynchronous sink ----
     import shutil
     import tempfile
-    n_sweep = 6
+    n_sweep = 12
     ring = [torch.tensor(p_, dtype=torch.float32) for p_ in synth.camera_ring(n_sweep * world)]
     tmp = tempfile.mkdtemp(prefix="nfb_sweep_")
     try:

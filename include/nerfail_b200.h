@@ -246,6 +246,15 @@ NFB_API int nfb_gauss_scatter_bwd(const float* g_x, const float* g_xrgba, const 
                           const uint8_t* ori, int64_t B, int64_t HW, float eps, int64_t T,
                           float* g_table, void* stream);
 
+/* replaces: model/GaussNet.py:121-145 — NHWC RGBA -> NCHW RGB, white where alpha is 0 (the classifier's input).
+ * img_f32 [B,HW,4] float or img_u8 [B,HW,4] uint8 (exactly one non-NULL); alpha_src [B,HW,4] float whose channel 3
+ * decides (NULL: the image's own channel 3); out [B,3,HW] = alpha > 0 ? rgb : fill (255 in the reference).
+ * nfb_chw_to_rgba is its adjoint (and, with fill = 0, its own second derivative): g_img [B,HW,4] =
+ * alpha > 0 ? (g_out[b,0..2,q], 0) : 0 — so the pair stays differentiable twice for deepfool.py:76-77.          */
+NFB_API int nfb_rgba_to_chw(const float* img_f32, const uint8_t* img_u8, const float* alpha_src, int64_t B, int64_t HW,
+                            float fill, float* out, void* stream);
+NFB_API int nfb_chw_to_rgba(const float* g_out, const float* alpha_src, int64_t B, int64_t HW, float* g_img, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

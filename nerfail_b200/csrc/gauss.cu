@@ -215,6 +215,43 @@ static int stream_grid(int64_t items) {
 
 }  // namespace nfb
 
+namespace nfb {
+
+// RGBA [B,HW,4] -> planar RGB [B,3,HW] on a white (fill) background: model/GaussNet.py:121-145
+//   cla = where(alpha > 0, rgb, 255) after the NHWC -> NCHW transpose (alpha = channel 3 of the same image).
+// One thread per pixel: a float4 (or uchar4) read, three coalesced plane writes.
+template <typename Pix>
+__global__ void __launch_bounds__(256)
+rgba_to_chw_kernel(const Pix* __restrict__ img, const float4* __restrict__ alpha_src, int64_t B, int64_t HW, float fill,
+                   float* __restrict__ out) {
+  const int64_t n = B * HW;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, q = p % HW;
+    const Pix v = img[p];
+    const float a = alpha_src ? alpha_src[p].w : (float)v.w;
+    const bool on = a > 0.f;
+    float* o = out + b * 3 * HW + q;
+    o[0] = on ? (float)v.x : fill;
+    o[HW] = on ? (float)v.y : fill;
+    o[2 * HW] = on ? (float)v.z : fill;
+  }
+}
+
+// adjoint of the above with fill = 0: g_img[b,q,c] = alpha > 0 ? g_out[b,c,q] : 0 (c < 3), g_img[b,q,3] = 0
+__global__ void __launch_bounds__(256)
+chw_to_rgba_kernel(const float* __restrict__ g_out, const float4* __restrict__ alpha_src, int64_t B, int64_t HW,
+                   float4* __restrict__ g_img) {
+  const int64_t n = B * HW;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, q = p % HW;
+    const bool on = alpha_src[p].w > 0.f;
+    const float* g = g_out + b * 3 * HW + q;
+    g_img[p] = on ? make_float4(g[0], g[HW], g[2 * HW], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+}  // namespace nfb
+
 extern "C" {
 
 int nfb_gauss_weights(const float* dist_idx, int64_t B, int64_t HW, float c, float* i_w, void* stream) {
@@ -264,6 +301,33 @@ int nfb_gauss_scatter_bwd(const float* g_x, const float* g_xrgba, const float* x
         reinterpret_cast<const float4*>(g_x), reinterpret_cast<const float4*>(g_xrgba),
         reinterpret_cast<const float4*>(x), w_idx, ori, B, HW, eps, T, reinterpret_cast<float4*>(g_table));
   return nfb::check_launch("gauss_scatter_bwd");
+}
+
+int nfb_rgba_to_chw(const float* img_f32, const uint8_t* img_u8, const float* alpha_src, int64_t B, int64_t HW, float fill,
+                    float* out, void* stream) {
+  NFB_REQUIRE((img_f32 != nullptr) != (img_u8 != nullptr) && out, "rgba_to_chw: exactly one of img_f32 / img_u8, and out");
+  NFB_REQUIRE(B >= 0 && HW >= 0, "rgba_to_chw: B=%lld HW=%lld", (long long)B, (long long)HW);
+  NFB_REQUIRE(((reinterpret_cast<uintptr_t>(img_f32) | reinterpret_cast<uintptr_t>(alpha_src)) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(img_u8) & 3) == 0, "rgba_to_chw: images must be 16-byte aligned (uint8: 4)");
+  if (B * HW == 0) return NFB_OK;
+  if (img_f32)
+    nfb::rgba_to_chw_kernel<float4><<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(img_f32), reinterpret_cast<const float4*>(alpha_src), B, HW, fill, out);
+  else
+    nfb::rgba_to_chw_kernel<uchar4><<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uchar4*>(img_u8), reinterpret_cast<const float4*>(alpha_src), B, HW, fill, out);
+  return nfb::check_launch("rgba_to_chw");
+}
+
+int nfb_chw_to_rgba(const float* g_out, const float* alpha_src, int64_t B, int64_t HW, float* g_img, void* stream) {
+  NFB_REQUIRE(g_out && alpha_src && g_img, "chw_to_rgba: null pointer");
+  NFB_REQUIRE(B >= 0 && HW >= 0, "chw_to_rgba: B=%lld HW=%lld", (long long)B, (long long)HW);
+  NFB_REQUIRE(((reinterpret_cast<uintptr_t>(alpha_src) | reinterpret_cast<uintptr_t>(g_img)) & 15) == 0,
+              "chw_to_rgba: images must be 16-byte aligned");
+  if (B * HW == 0) return NFB_OK;
+  nfb::chw_to_rgba_kernel<<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
+      g_out, reinterpret_cast<const float4*>(alpha_src), B, HW, reinterpret_cast<float4*>(g_img));
+  return nfb::check_launch("chw_to_rgba");
 }
 
 }  // extern "C"

@@ -97,16 +97,17 @@ class gauss_net(nn.Module):
 
     @staticmethod
     def _to_classifier_input(img_bhwc):
-        """RGBA -> NCHW RGB on white (reference :121-145)."""
-        chw = img_bhwc.permute(0, 3, 1, 2)
-        rgb, a = chw[:, :3], chw[:, 3:4]
-        return torch.where(a > 0, rgb, torch.full_like(rgb, 255.0))
+        """RGBA -> NCHW RGB on white (reference :121-145): one kernel (nfb_rgba_to_chw), differentiable twice."""
+        if img_bhwc.dtype == torch.uint8:
+            return ops.rgba_u8_to_chw(img_bhwc)
+        return ops.RgbaToChwFn.apply(img_bhwc, 255.0)
 
     def forward(self, spatial_rgb, weight_and_index_list, ori_img, zero_init_mask: bool = False):
         x, x_rgba = self.perturbed(spatial_rgb, weight_and_index_list, ori_img)
         ori_f = ori_img.float() if isinstance(ori_img, torch.Tensor) else torch.tensor(ori_img, dtype=torch.float)
         cla_x = self._to_classifier_input(x_rgba)
-        cla_ori = self._to_classifier_input(ori_f)
+        cla_ori = self._to_classifier_input(ori_img if isinstance(ori_img, torch.Tensor) and ori_img.dtype == torch.uint8 and ori_img.is_cuda
+                                            else ori_f)
         if self.model_name != "my_model":
             size = 224 if self.model_name == "vit_b_16" else 299
             from torchvision.transforms import Resize

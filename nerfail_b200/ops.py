@@ -521,6 +521,58 @@ class GaussGatherFn(torch.autograd.Function):
         return g, None, None, None, None
 
 
+class RgbaToChwFn(torch.autograd.Function):
+    """Classifier input of model/GaussNet.py:121-145: [B,H,W,4] RGBA -> [B,3,H,W] RGB, `fill` where alpha (channel 3 of
+    the image itself) is 0.  Backward = ChwToRgbaFn, whose backward is this op with fill 0: differentiable twice."""
+
+    @staticmethod
+    def forward(ctx, img, fill):
+        img = _f32(img)
+        B, H, W, _ = img.shape
+        out = torch.empty((B, 3, H, W), dtype=torch.float32, device=img.device)
+        with torch.cuda.device(img.device):
+            check(_lib.load().nfb_rgba_to_chw(ptr(img), None, None, B, H * W, float(fill), ptr(out), stream()), "nfb_rgba_to_chw")
+        ctx.save_for_backward(img)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (img,) = ctx.saved_tensors
+        return ChwToRgbaFn.apply(g_out, img), None
+
+
+class ChwToRgbaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g_out, alpha_src):
+        g_out = _f32(g_out)
+        B, _, H, W = g_out.shape
+        g_img = torch.empty((B, H, W, 4), dtype=torch.float32, device=g_out.device)
+        with torch.cuda.device(g_out.device):
+            check(_lib.load().nfb_chw_to_rgba(ptr(g_out), ptr(alpha_src), B, H * W, ptr(g_img), stream()), "nfb_chw_to_rgba")
+        ctx.save_for_backward(alpha_src)
+        return g_img
+
+    @staticmethod
+    def backward(ctx, gg_img):
+        (alpha_src,) = ctx.saved_tensors
+        gg = _f32(gg_img)
+        B, H, W, _ = gg.shape
+        out = torch.empty((B, 3, H, W), dtype=torch.float32, device=gg.device)
+        with torch.cuda.device(gg.device):
+            check(_lib.load().nfb_rgba_to_chw(ptr(gg), None, ptr(alpha_src), B, H * W, 0.0, ptr(out), stream()), "nfb_rgba_to_chw")
+        return out, None
+
+
+def rgba_u8_to_chw(img_u8: torch.Tensor, fill: float = 255.0) -> torch.Tensor:
+    """The same conversion for the original uint8 image (no gradient): [B,H,W,4] uint8 -> [B,3,H,W] float32."""
+    img_u8 = img_u8.contiguous()
+    B, H, W, _ = img_u8.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=img_u8.device)
+    with torch.cuda.device(img_u8.device):
+        check(_lib.load().nfb_rgba_to_chw(None, ptr(img_u8), None, B, H * W, float(fill), ptr(out), stream()), "nfb_rgba_to_chw")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # bf16 tile images + tensor-core weight gradient
 # ------------------------------------------------------------------------------------------------

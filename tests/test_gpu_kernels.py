@@ -243,6 +243,38 @@ def test_gauss_full_forward_signature_and_double_backward(cuda):
     assert g2 is None or torch.isfinite(g2).all()
 
 
+def test_classifier_input_conversion_and_its_derivatives(cuda):
+    """nfb_rgba_to_chw / nfb_chw_to_rgba (model/GaussNet.py:121-145: NHWC RGBA -> NCHW RGB, 255 where alpha is 0) against the
+    reference's torch expression: values bit-exact (float and uint8 image), first and second derivative exact."""
+    from nerfail_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    img = (torch.rand(2, 13, 7, 4, generator=g) * 255)
+    img[..., 3] = torch.where(torch.rand(2, 13, 7, generator=g) < 0.4, torch.zeros(()), img[..., 3])
+
+    def ref(t):
+        chw = t.permute(0, 3, 1, 2)
+        return torch.where(chw[:, 3:4] > 0, chw[:, :3], torch.full_like(chw[:, :3], 255.0))
+    a = img.clone().to(cuda).requires_grad_(True)
+    b = img.clone().requires_grad_(True)
+    ya, yb = ops.RgbaToChwFn.apply(a, 255.0), ref(b)
+    assert torch.equal(ya.detach().cpu(), yb.detach())
+    u8 = img.to(torch.uint8)
+    assert torch.equal(ops.rgba_u8_to_chw(u8.to(cuda)).cpu(), ref(u8.float()))
+    w = torch.randn(yb.shape, generator=g)
+    ga = torch.autograd.grad((ya * w.to(cuda)).sum(), a, create_graph=True)[0]
+    gb = torch.autograd.grad((yb * w).sum(), b, create_graph=True)[0]
+    assert torch.equal(ga.detach().cpu(), gb.detach())
+    # the gradient is linear in the upstream gradient: differentiate <ga, v> with respect to it
+    wa = w.clone().to(cuda).requires_grad_(True)
+    wb = w.clone().requires_grad_(True)
+    v = torch.randn(img.shape, generator=g)
+    ga2 = torch.autograd.grad((ops.RgbaToChwFn.apply(a, 255.0) * wa).sum(), a, create_graph=True)[0]
+    gb2 = torch.autograd.grad((ref(b) * wb).sum(), b, create_graph=True)[0]
+    ha = torch.autograd.grad((ga2 * v.to(cuda)).sum(), wa)[0]
+    hb = torch.autograd.grad((gb2 * v).sum(), wb)[0]
+    assert torch.equal(ha.cpu(), hb)
+
+
 def test_knn8_bit_exact_indices(cuda):
     from nerfail_b200 import ops
     g = golden("knn.npz")
