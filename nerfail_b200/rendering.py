@@ -79,6 +79,7 @@ class NetworkQuery:
         if ray_batch.shape[-1] == 11 and _fusable(network_fn, self.embed_fn, self.embeddirs_fn):
             return network_fn.fused().forward_rays(ray_batch, z_vals)
         if (ray_batch.shape[-1] == 11 and torch.is_grad_enabled() and nerf.train_precision() == "bf16"
+                and not ray_batch.requires_grad and not z_vals.requires_grad      # the fused backward reaches the parameters only
                 and isinstance(network_fn, NeRF) and network_fn.fused_supported()
                 and isinstance(self.embed_fn, nerf.Embedder) and self.embed_fn.multires == 10
                 and isinstance(self.embeddirs_fn, nerf.Embedder) and self.embeddirs_fn.multires == 4):

@@ -125,11 +125,12 @@ def test_fp32_linear_primitives_ragged(cuda):
             assert err < 1e-4 * (float(want.abs().max()) + 1e-6), (M, N, K, name, err)
 
 
-def test_training_step_gradients_vs_reference_golden(cuda):
+def test_training_step_gradients_vs_reference_golden(cuda, monkeypatch):
     """BASELINE config 5 in miniature: render_rays forward + backward through both networks (fp32 path), stratified
     + inverse-CDF sampling with the reference's pytest-hook draws (configs/lego.txt trains with perturb = 1), loss =
     mse(fine) + mse(coarse) (run_nerf.py:776-791).  Parameter gradients within 1e-3 relative of the reference's."""
     import nerfail_b200 as nb
+    monkeypatch.setenv("NERFAIL_B200_TRAIN", "fp32")           # the exact-parity training path (default is bf16)
     g = golden("train_step.npz")
     nets = []
     for seed in (0, 1):
