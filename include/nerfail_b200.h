@@ -204,6 +204,19 @@ NFB_API int nfb_sample_pdf(const float* bins, const float* weights, int w_pitch,
 NFB_API int nfb_hierarchical(const float* z_coarse, const float* weights, const float* u, int R, int Sc, int N,
                      float* z_fine, float* z_samples, float* z_std, void* stream);
 
+/* One ray batch, coarse + fine, without autograd: the whole kernel sequence of render_rays in one call.
+ * replaces: run_nerf.py:308-418 (render_rays; nerf_to_coord.py:320-433 when pts_max != NULL) under torch.no_grad() with
+ * raw_noise_std = 0: coarse depths -> fused MLP -> compositing -> inverse-CDF resampling + merge -> fused MLP -> compositing.
+ * rays [R,11]; t_rand [R,N_samples] / u [R,N_importance] uniform numbers or NULL (perturb == 0);
+ * outputs rgb [R,3], disp [R], acc [R] (+ rgb0 / disp0 / acc0 / z_std [R] when N_importance > 0, else ignored),
+ * pts_max [R,3] or NULL.  fine may be NULL (the coarse network is queried twice, run_nerf.py:399).
+ * workspace: nfb_render_rays_workspace_bytes(R, N_samples, N_importance) bytes, 256-byte aligned, caller-owned.     */
+NFB_API size_t nfb_render_rays_workspace_bytes(int R, int N_samples, int N_importance);
+NFB_API int nfb_render_rays_fwd(const nfb_mlp_t* coarse, const nfb_mlp_t* fine, const float* rays, int R, int N_samples,
+                                int N_importance, int lindisp, int white_bkgd, const float* t_rand, const float* u,
+                                float* rgb, float* disp, float* acc, float* rgb0, float* disp0, float* acc0, float* z_std,
+                                float* pts_max, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* B. GaussNet path                                                            */
 /* ------------------------------------------------------------------------- */

@@ -48,4 +48,44 @@ int nfb_device_cc(void) {
   return major * 10 + minor;
 }
 
+// ---- one ray batch, coarse + fine, without autograd: the kernel sequence of render_rays in one call ----
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+size_t nfb_render_rays_workspace_bytes(int R, int N_samples, int N_importance) {
+  if (R <= 0 || N_samples <= 0 || N_importance < 0) return 0;
+  const size_t Sc = (size_t)N_samples, Sf = Sc + (size_t)N_importance, r = (size_t)R;
+  // z_coarse, raw (sized for the fine pass, reused), weights (fine size, reused), z_fine
+  return align256(r * Sc * 4) + align256(r * Sf * 16) + align256(r * Sf * 4) + align256(r * Sf * 4);
+}
+
+int nfb_render_rays_fwd(const nfb_mlp_t* coarse, const nfb_mlp_t* fine, const float* rays, int R, int N_samples,
+                        int N_importance, int lindisp, int white_bkgd, const float* t_rand, const float* u,
+                        float* rgb, float* disp, float* acc, float* rgb0, float* disp0, float* acc0, float* z_std,
+                        float* pts_max, void* workspace, size_t workspace_bytes, void* stream) {
+  NFB_REQUIRE(coarse && rays && rgb && disp && acc, "render_rays_fwd: null pointer");
+  NFB_REQUIRE(N_importance == 0 || (rgb0 && disp0 && acc0), "render_rays_fwd: coarse outputs are required when N_importance > 0");
+  NFB_REQUIRE(R >= 0 && N_samples >= 1 && N_importance >= 0, "render_rays_fwd: R=%d N_samples=%d N_importance=%d", R, N_samples, N_importance);
+  if (R == 0) return NFB_OK;
+  NFB_REQUIRE(workspace && workspace_bytes >= nfb_render_rays_workspace_bytes(R, N_samples, N_importance) &&
+              (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "render_rays_fwd: workspace too small or not 256-byte aligned");
+  const size_t Sc = (size_t)N_samples, Sf = Sc + (size_t)N_importance, r = (size_t)R;
+  char* w = static_cast<char*>(workspace);
+  float* z_c = reinterpret_cast<float*>(w);  w += align256(r * Sc * 4);
+  float* raw = reinterpret_cast<float*>(w);  w += align256(r * Sf * 16);
+  float* wts = reinterpret_cast<float*>(w);  w += align256(r * Sf * 4);
+  float* z_f = reinterpret_cast<float*>(w);
+  int rc = nfb_coarse_z(rays, R, N_samples, lindisp, t_rand, z_c, stream);                            // run_nerf.py:357-379
+  if (rc == NFB_OK) rc = nfb_mlp_fwd(coarse, 1, nullptr, nullptr, rays, z_c, R, N_samples, raw, stream);   // :381-385
+  const bool two = N_importance > 0;
+  if (rc == NFB_OK)                                                                                     // :386
+    rc = nfb_composite_fwd(raw, z_c, rays + 3, 11, nullptr, R, N_samples, white_bkgd, two ? rgb0 : rgb, two ? disp0 : disp,
+                           two ? acc0 : acc, wts, nullptr, two ? nullptr : pts_max, stream);
+  if (rc != NFB_OK || !two) return rc;
+  rc = nfb_hierarchical(z_c, wts, u, R, N_samples, N_importance, z_f, nullptr, z_std, stream);         // :392-396, :412
+  if (rc == NFB_OK) rc = nfb_mlp_fwd(fine ? fine : coarse, 1, nullptr, nullptr, rays, z_f, R, (int)Sf, raw, stream);   // :397-401
+  if (rc == NFB_OK)                                                                                     // :403, nerf_to_coord.py:418-421
+    rc = nfb_composite_fwd(raw, z_f, rays + 3, 11, nullptr, R, (int)Sf, white_bkgd, rgb, disp, acc, wts, nullptr, pts_max, stream);
+  return rc;
+}
+
 }  // extern "C"

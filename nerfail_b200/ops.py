@@ -521,6 +521,36 @@ class GaussGatherFn(torch.autograd.Function):
         return g, None, None, None, None
 
 
+def render_rays_fused(coarse: "FusedMLP", fine: Optional["FusedMLP"], rays: torch.Tensor, N_samples: int, N_importance: int,
+                      lindisp: bool, white_bkgd: bool, t_rand=None, u=None, want_pts_max: bool = False) -> dict:
+    """nfb_render_rays_fwd: the whole no-grad kernel sequence of render_rays (run_nerf.py:308-418) for one ray batch in one
+    C call (coarse depths, fused MLP, compositing, resampling + merge, fused MLP, compositing [+ pts_max])."""
+    lib = _lib.load()
+    rays = _f32(rays)
+    R = rays.shape[0]
+    dev = rays.device
+    f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+    out = {"rgb_map": f(R, 3), "disp_map": f(R), "acc_map": f(R)}
+    two = N_importance > 0
+    if two:
+        out.update(rgb0=f(R, 3), disp0=f(R), acc0=f(R), z_std=f(R))
+    if want_pts_max:
+        out["pts_max"] = f(R, 3)
+    if R == 0:
+        return out
+    nbytes = int(lib.nfb_render_rays_workspace_bytes(R, N_samples, N_importance))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    t_rand = _f32(t_rand) if t_rand is not None else None
+    u = _f32(u) if u is not None else None
+    with torch.cuda.device(dev):
+        check(lib.nfb_render_rays_fwd(coarse._h, fine._h if fine is not None else None, ptr(rays), R, N_samples, N_importance,
+                                      int(bool(lindisp)), int(bool(white_bkgd)), ptr(t_rand), ptr(u),
+                                      ptr(out["rgb_map"]), ptr(out["disp_map"]), ptr(out["acc_map"]),
+                                      ptr(out.get("rgb0")), ptr(out.get("disp0")), ptr(out.get("acc0")), ptr(out.get("z_std")),
+                                      ptr(out.get("pts_max")), ptr(ws), nbytes, stream()), "nfb_render_rays_fwd")
+    return out
+
+
 class RgbaToChwFn(torch.autograd.Function):
     """Classifier input of model/GaussNet.py:121-145: [B,H,W,4] RGBA -> [B,3,H,W] RGB, `fill` where alpha (channel 3 of
     the image itself) is 0.  Backward = ChwToRgbaFn, whose backward is this op with fill 0: differentiable twice."""

@@ -110,6 +110,20 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     """run_nerf.py:308-418 (and nerf_to_coord.py:320-433 when with_pts_max=True)."""
     ray_batch = ray_batch.float().contiguous()
     N_rays = ray_batch.shape[0]
+    # Whole-batch fast path: without autograd, noise and the raw output nothing but kernel launches is left of this
+    # function, so they are sequenced by ONE C call (nfb_render_rays_fwd); NERFAIL_B200_RENDER_RAYS=ops keeps the per-op path.
+    if (not torch.is_grad_enabled() and not retraw and raw_noise_std == 0. and not pytest and ray_batch.shape[-1] == 11
+            and isinstance(network_query_fn, NetworkQuery)
+            and _fusable(network_fn, network_query_fn.embed_fn, network_query_fn.embeddirs_fn)
+            and (network_fine is None or _fusable(network_fine, network_query_fn.embed_fn, network_query_fn.embeddirs_fn))
+            and 3 <= N_samples <= 128 and N_samples + N_importance <= 512
+            and os.environ.get("NERFAIL_B200_RENDER_RAYS", "fused") != "ops"):
+        dev = ray_batch.device
+        t_r = torch.rand((N_rays, N_samples), device=dev) if perturb > 0. else None
+        u_r = torch.rand((N_rays, N_importance), device=dev) if (perturb != 0. and N_importance > 0) else None
+        fine = network_fine.fused() if network_fine is not None else None
+        return ops.render_rays_fused(network_fn.fused(), fine, ray_batch, N_samples, N_importance, lindisp, white_bkgd,
+                                     t_r, u_r, want_pts_max=with_pts_max)
     t_rand = None
     if perturb > 0.:
         if pytest:

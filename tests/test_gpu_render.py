@@ -384,3 +384,30 @@ def test_graphed_train_step_equals_eager(cuda, monkeypatch):
     for k in sd0:
         moved = float((sd0[k].cpu().double() - init[k].double()).norm())
         assert float((sd0[k].double() - sd1[k].double()).norm()) < 0.3 * moved + 1e-12, k
+
+
+def test_render_rays_single_call_equals_op_sequence(cuda, monkeypatch):
+    """nfb_render_rays_fwd (one C call per ray batch) against the per-op sequence it replaces (NERFAIL_B200_RENDER_RAYS=ops):
+    the same kernels in the same order, so every output is bit-identical — deterministic and stratified sampling (same
+    torch generator draws), with and without the fine network / pts_max, ragged batch sizes."""
+    import nerfail_b200 as nb
+    _, kw = make_kwargs(cuda)
+    K, _ = synth.intrinsics(30, 30)
+    rays = no.camera_rays(30, 30, K, torch.tensor(synth.pose_spherical(40.0, -30.0, 4.0)[:3, :4]), 2.0, 6.0).to(cuda)
+    base = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc", "perturb", "N_importance", "network_fine")}
+    cases = [dict(perturb=0., N_importance=128, network_fine=kw["network_fine"], n=900, pm=True),
+             dict(perturb=1., N_importance=128, network_fine=kw["network_fine"], n=517, pm=False),
+             dict(perturb=0., N_importance=64, network_fine=None, n=33, pm=True),
+             dict(perturb=1., N_importance=0, network_fine=None, n=1, pm=True)]
+    with torch.no_grad():
+        for c in cases:
+            outs = []
+            for mode in ("fused", "ops"):
+                monkeypatch.setenv("NERFAIL_B200_RENDER_RAYS", mode)
+                torch.manual_seed(5)
+                outs.append(nb.render_rays(rays[:c["n"]], perturb=c["perturb"], N_importance=c["N_importance"],
+                                           network_fine=c["network_fine"], with_pts_max=c["pm"], **base))
+            a, b = outs
+            assert set(a) == set(b), (sorted(a), sorted(b))
+            for k in a:
+                assert torch.equal(a[k], b[k]), (k, c["n"])
