@@ -350,3 +350,27 @@ def test_mlp_bwd_overlapped_equals_serial(cuda):
         assert torch.equal(dy_a.view(torch.int16), dy_b.view(torch.int16))
         scale = float(grad_a.abs().max())
         assert float((grad_a - grad_b).abs().max()) < 1e-4 * scale, rep
+
+
+@pytest.mark.parametrize("R,S", [(5, 100), (3, 64), (45, 192)])
+def test_head_weight_gradients_are_exact_side_sums(cuda, R, S):
+    """alpha_linear / rgb_linear gradients come from fp32 side sums of g_raw against the saved bf16 images (wgrad.cu), not
+    from tensor-core products: against the same sums in float64 from the saved images they agree to fp32 rounding, for
+    batch sizes that end inside a 64-row stage (M % 64 != 0), inside a tile and on a tile boundary."""
+    from nerfail_b200 import ops
+    net, rays, z = _train_setup(cuda, R=R, S=S, seed=7)
+    M = R * S
+    cot = torch.randn(R, S, 4, generator=torch.Generator().manual_seed(M)).to(cuda)
+    raw = net.forward_rays_train(rays, z)
+    act, _ = raw.grad_fn.saved_tensors
+    (raw * cot).sum().backward()
+    net.fused().status()
+    flat = ops.from_tile_image(act)[:M].double()             # [M, 40 * 64]
+    g = cot.reshape(M, 4).double()
+    h7, hv = flat[:, 28 * 64:32 * 64], flat[:, 36 * 64:38 * 64]
+    want = {"alpha_linear.weight": (g[:, 3:4].t() @ h7), "alpha_linear.bias": g[:, 3].sum().reshape(1),
+            "rgb_linear.weight": (g[:, 0:3].t() @ hv), "rgb_linear.bias": g[:, 0:3].sum(0)}
+    got = dict(net.named_parameters())
+    for name, w in want.items():
+        err = float((got[name].grad.double() - w).abs().max())
+        assert err < 2e-5 * float(w.abs().max()) + 1e-6, (name, err, float(w.abs().max()))
