@@ -381,6 +381,24 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
                              "ms_per_view_per_rank": ms_sweep / n_sweep, "scaling": "weak", "timing": "host wall clock incl. file writes, max over ranks"}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+    # ---- Blender loader (load_blender.py:37-110): 48 RGBA PNGs of 800x800, thread-pool decode vs one after the other ----
+    if rank == 0:
+        from nerfail_b200 import data as ndata
+        tmp = tempfile.mkdtemp(prefix="nfb_scene_")
+        try:
+            synth.write_blender_scene(tmp, 800, 800, (16, 16, 16), seed=0)
+            t0 = time.perf_counter()
+            imgs, poses, _, hwf, _ = ndata.load_blender_data(tmp, half_res=False, testskip=1)
+            t_pool = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            ndata.load_blender_data(tmp, half_res=False, testskip=1, workers=1)
+            t_serial = time.perf_counter() - t0
+            out["blender_loader"] = {"metric": "load_blender_data, 48 RGBA PNGs of 800x800 (incompressible noise images: worst case for the decoder)",
+                                     "images_per_s": imgs.shape[0] / t_pool, "seconds": t_pool, "seconds_one_thread": t_serial,
+                                     "threads": min(32, os.cpu_count() or 1)}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
     return out
 
 

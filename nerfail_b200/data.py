@@ -67,12 +67,25 @@ def load_blender_data(basedir, half_res=False, testskip=1, train_dir=None, worke
             poses.append(np.array(frame['transform_matrix']))
         jobs.append(names)
         poses_by_split.append(np.array(poses).astype(np.float32))
+    # decode AND normalise on the pool: (uint8 / 255.) evaluated in float64 and rounded to float32 straight into the
+    # split's output array is the reference's (np.array(imgs) / 255.).astype(np.float32) element for element, without
+    # its float64 temporary and without a stacking copy (numpy and cv2 release the GIL inside all three steps)
+    def _normalise(job):
+        dst, img = job
+        np.divide(img, 255., out=dst, dtype=np.float64, casting='unsafe')
     with ThreadPoolExecutor(max_workers=workers or min(32, os.cpu_count() or 1)) as pool:
-        decoded = [list(pool.map(_imread_rgba, names)) for names in jobs]
+        decoded = []
+        for names in jobs:
+            raw = list(pool.map(_imread_rgba, names))
+            if not raw:
+                decoded.append(np.zeros((0,), np.float32))
+                continue
+            arr = np.empty((len(raw),) + raw[0].shape, np.float32)
+            list(pool.map(_normalise, [(arr[i], im) for i, im in enumerate(raw)]))
+            decoded.append(arr)
 
     all_imgs, train_imgs, counts = [], [], [0]
-    for s, imgs in zip(splits, decoded):
-        imgs = (np.array(imgs) / 255.).astype(np.float32)          # keep all 4 channels (RGBA)
+    for s, imgs in zip(splits, decoded):                            # keep all 4 channels (RGBA)
         counts.append(counts[-1] + imgs.shape[0])
         if s == 'train' and train_dir is not None:
             train_imgs.append(imgs)
