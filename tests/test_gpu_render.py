@@ -411,3 +411,26 @@ def test_render_rays_single_call_equals_op_sequence(cuda, monkeypatch):
             assert set(a) == set(b), (sorted(a), sorted(b))
             for k in a:
                 assert torch.equal(a[k], b[k]), (k, c["n"])
+
+
+def test_bf16_training_tracks_fp32_training_within_psnr_budget(cuda):
+    """The tensor-core training path (default) against the fp32 exact path on the same fitting problem (student NeRF fitted
+    to views rendered from a teacher NeRF, same initial weights, same ray batches, scripts/train_convergence.py): the loss
+    curves agree to 1 % at every logged step and a held-out view rendered from the two students differs by a fraction of a
+    dB with either sign (measured: bf16 - fp32 = -0.012 dB after 200 steps of 1024 rays, +0.061 dB after 120 steps of 512
+    rays: step-to-step noise of two fp32-different trajectories, not a bias; bound 0.15 dB)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import train_convergence as tc
+    prev = os.environ.get("NERFAIL_B200_TRAIN")
+    try:
+        l16, p16 = tc.run("bf16", 200, 1024, cuda, log=False)
+        l32, p32 = tc.run("fp32", 200, 1024, cuda, log=False)
+    finally:
+        if prev is None:
+            os.environ.pop("NERFAIL_B200_TRAIN", None)
+        else:
+            os.environ["NERFAIL_B200_TRAIN"] = prev
+    assert l16[-1] < 0.25 * l16[0], l16                       # it actually learns
+    assert np.allclose(l16, l32, rtol=1e-2), (l16, l32)
+    assert abs(p16 - p32) < 0.15, (p16, p32)
