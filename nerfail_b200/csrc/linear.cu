@@ -27,10 +27,59 @@ struct GemmArgs {
   int64_t r_per_split;               // split-r: block z handles r in [z*r_per_split, ...), C advances by I*ldc per split
 };
 
-// A_RC / B_RC: reduction index is the contiguous one for that operand.
+// One group = 4 consecutive elements of an operand tile along its CONTIGUOUS dimension, zero-filled outside the matrix
+// (and where the relu mask says so).  RC (reduction index contiguous): group q of 512 = row q / 4, reduction offsets
+// (q % 4) * 4 ..; otherwise: reduction row q / 32, output offsets (q % 32) * 4 ...  `vec` (pointer and pitch 16-byte
+// aligned) takes the 128-bit load when the whole group lies inside the matrix.
+template <bool RC, bool MASK>
+__device__ __forceinline__ float4 load_group(const float* __restrict__ P, int64_t ld, const float* __restrict__ Mk, int64_t ldm,
+                                             int64_t o0, int64_t extent, int64_t r0, int64_t r_end, int q, bool vec) {
+  int64_t go, gr;                       // first element: output index, reduction index
+  if (RC) { go = o0 + (q >> 2); gr = r0 + ((q & 3) << 2); } else { gr = r0 + (q >> 5); go = o0 + ((q & 31) << 2); }
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t off = RC ? go * ld + gr : gr * ld + go;
+  const bool inside = RC ? (go < extent && gr + 3 < r_end) : (gr < r_end && go + 3 < extent);
+  if (vec && inside) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(P + off));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    if (MASK) {
+      const int64_t moff = RC ? go * ldm + gr : gr * ldm + go;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (!(__ldg(Mk + moff + c) > 0.f)) v[c] = 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool ok = RC ? (go < extent && gr + c < r_end) : (gr < r_end && go + c < extent);
+      if (ok) {
+        v[c] = __ldg(P + off + c);
+        if (MASK) {
+          const int64_t moff = RC ? go * ldm + gr : gr * ldm + go;
+          if (!(__ldg(Mk + moff + c) > 0.f)) v[c] = 0.f;
+        }
+      }
+    }
+  }
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+
+template <bool RC>
+__device__ __forceinline__ void store_group(float (*S)[BM + PAD], int q, const float4 v) {
+  if (RC) {
+    const int oo = q >> 2, rr = (q & 3) << 2;
+    S[rr][oo] = v.x; S[rr + 1][oo] = v.y; S[rr + 2][oo] = v.z; S[rr + 3][oo] = v.w;
+  } else {
+    *reinterpret_cast<float4*>(&S[q >> 5][(q & 31) << 2]) = v;
+  }
+}
+
+// A_RC / B_RC: reduction index is the contiguous one for that operand.  The next K-slab is fetched into registers
+// (128-bit loads where alignment allows) while the current one is multiplied out of shared memory; the products are
+// accumulated in ascending reduction order whatever the tiling, so results do not depend on it.
 template <bool A_RC, bool B_RC, bool MASK>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_kernel(GemmArgs g) {
+  static_assert(BM == BN, "operand tiles share the loader");
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x;
@@ -38,41 +87,31 @@ gemm_kernel(GemmArgs g) {
   const int64_t r_begin = (int64_t)blockIdx.z * g.r_per_split;
   const int64_t r_end = min(g.Rn, r_begin + g.r_per_split);
   const int ty = tid / 16, tx = tid % 16;     // 16 x 16 threads, 8 x 8 outputs each
+  const bool vecA = ((reinterpret_cast<uintptr_t>(g.A) | (uintptr_t)(g.lda * 4)) & 15) == 0;
+  const bool vecB = ((reinterpret_cast<uintptr_t>(g.B) | (uintptr_t)(g.ldb * 4)) & 15) == 0;
   float acc[8][8];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
 
+  float4 pa[2], pb[2];
+  auto fetch = [&](int64_t r0) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      pa[e] = load_group<A_RC, MASK>(g.A, g.lda, g.Amask, g.ldm, i0, g.I, r0, r_end, tid + e * GEMM_THREADS, vecA);
+      pb[e] = load_group<B_RC, false>(g.B, g.ldb, nullptr, 0, j0, g.J, r0, r_end, tid + e * GEMM_THREADS, vecB);
+    }
+  };
+  if (r_begin < r_end) fetch(r_begin);
   for (int64_t r0 = r_begin; r0 < r_end; r0 += BK) {
 #pragma unroll
-    for (int e = 0; e < (BM * BK) / GEMM_THREADS; ++e) {
-      const int idx = tid + e * GEMM_THREADS;
-      int ii, rr;
-      if (A_RC) { ii = idx / BK; rr = idx % BK; } else { rr = idx / BM; ii = idx % BM; }
-      const int64_t gi = i0 + ii, gr = r0 + rr;
-      float v = 0.f;
-      if (gi < g.I && gr < r_end) {
-        const int64_t off = A_RC ? gi * g.lda + gr : gr * g.lda + gi;
-        v = __ldg(g.A + off);
-        if (MASK) {
-          const int64_t moff = A_RC ? gi * g.ldm + gr : gr * g.ldm + gi;
-          if (!(__ldg(g.Amask + moff) > 0.f)) v = 0.f;
-        }
-      }
-      As[rr][ii] = v;
-    }
-#pragma unroll
-    for (int e = 0; e < (BN * BK) / GEMM_THREADS; ++e) {
-      const int idx = tid + e * GEMM_THREADS;
-      int jj, rr;
-      if (B_RC) { jj = idx / BK; rr = idx % BK; } else { rr = idx / BN; jj = idx % BN; }
-      const int64_t gj = j0 + jj, gr = r0 + rr;
-      float v = 0.f;
-      if (gj < g.J && gr < r_end) v = __ldg(g.B + (B_RC ? gj * g.ldb + gr : gr * g.ldb + gj));
-      Bs[rr][jj] = v;
+    for (int e = 0; e < 2; ++e) {
+      store_group<A_RC>(As, tid + e * GEMM_THREADS, pa[e]);
+      store_group<B_RC>(Bs, tid + e * GEMM_THREADS, pb[e]);
     }
     __syncthreads();
+    if (r0 + BK < r_end) fetch(r0 + BK);
 #pragma unroll
     for (int rr = 0; rr < BK; ++rr) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[rr][ty * 8]);
