@@ -47,7 +47,8 @@ struct TrainArgs {
   int* ready;                     // [ntiles] or null (MODE_BWD): published count of landed store groups per tile, for a
                                   // concurrently running wgrad_kernel in consumer mode: 1 = dY_views,
                                   // 1 + b = output of backward step b - 1 as well (10 = everything)
-  int skip;                       // profiling only (NERFAIL_B200_TRAIN_SKIP): bit 0 = no mask stores, bit 1 = no image stores
+  int skip;                       // profiling only (NERFAIL_B200_TRAIN_SKIP): bit 0 = no mask stores, bit 1 = no image stores,
+                                  // bit 2 = image stores are not waited for before their source is overwritten (WRONG results: timing only)
   char* dy_img;                   // [ntiles][39][16 KB]  written by MODE_BWD
 };
 
@@ -272,7 +273,7 @@ mlp_train_kernel(const TrainArgs a) {
       char* dy_tile = (MODE == MODE_BWD) ? a.dy_img + tile * (int64_t)BWD_CHUNKS * CHUNK_BYTES : nullptr;
       uint32_t* mask_tile = a.mask + tile * (int64_t)MASK_WORDS_PER_TILE;
       // every bulk store of the previous unit must have finished READING shared memory before it is rewritten
-      if (tslot == 0) bulk_wait_read();
+      if (tslot == 0 && !(skip & 4)) bulk_wait_read();
       slot_sync();
 
       float vx = 0.f, vy = 0.f, vz = 0.f, gsig = 0.f;
@@ -337,7 +338,7 @@ mlp_train_kernel(const TrainArgs a) {
         // step must be done reading shared memory; the younger one is waited for half a drain later (cc == 2).  The
         // stores are HBM-bound (64 KB per slot and step), so this doubles the time they have before they stall the drain.
         const bool wait_all = (MODE == MODE_BWD && s == 0) || (MODE == MODE_FWD && s == 9);   // previous group read chunks 0/1
-        if (tslot == 0) { if (wait_all) bulk_wait_read(); else bulk_wait_read_but_last(); }
+        if (tslot == 0 && !(skip & 4)) { if (wait_all) bulk_wait_read(); else bulk_wait_read_but_last(); }
         if (AUX && MODE == MODE_BWD && ready && tslot == 0 && s >= 1) {
           // committed so far: the input-stage group and two groups per finished step; all but the last two have landed
           bulk_wait_all_but_two();
@@ -415,7 +416,7 @@ mlp_train_kernel(const TrainArgs a) {
         for (int cc = 0; cc < 4; ++cc) {
           if (cc == 2) {
             fence_proxy_async();
-            if (tslot == 0) bulk_wait_read();
+            if (tslot == 0 && !(skip & 4)) bulk_wait_read();
             slot_sync();                               // chunks 0 and 2 are final; chunks 1 and 3 may be overwritten
             if (tslot == 0 && !(skip & 2)) {
               char* dst = (MODE == MODE_FWD) ? act_tile + (int64_t)(s * 4) * CHUNK_BYTES : dy_tile + (int64_t)dy_chunk0(s) * CHUNK_BYTES;
