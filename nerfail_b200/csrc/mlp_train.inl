@@ -48,7 +48,8 @@ struct TrainArgs {
                                   // concurrently running wgrad_kernel in consumer mode: 1 = dY_views,
                                   // 1 + b = output of backward step b - 1 as well (10 = everything)
   int skip;                       // profiling only (NERFAIL_B200_TRAIN_SKIP): bit 0 = no mask stores, bit 1 = no image stores,
-                                  // bit 2 = image stores are not waited for before their source is overwritten (WRONG results: timing only)
+                                  // bit 2 = image stores are not waited for before their source is overwritten, bit 3 = every CTA
+                                  // rewrites the same two tile images, so the stores never leave L2 (both WRONG results: timing only)
   char* dy_img;                   // [ntiles][39][16 KB]  written by MODE_BWD
 };
 
@@ -269,8 +270,9 @@ mlp_train_kernel(const TrainArgs a) {
       const int64_t m = unit * ROWS_PER_UNIT + (int64_t)g * (TILE_M * CG) + rank * TILE_M + row;
       const int64_t tile = (unit * 2 + g) * CG + rank;          // = m / 128
       const bool live = m < a.M;
-      char* act_tile = (MODE == MODE_FWD) ? a.act_img + tile * (int64_t)FWD_CHUNKS * CHUNK_BYTES : nullptr;
-      char* dy_tile = (MODE == MODE_BWD) ? a.dy_img + tile * (int64_t)BWD_CHUNKS * CHUNK_BYTES : nullptr;
+      const int64_t img_tile = (skip & 8) ? (int64_t)(blockIdx.x * 2 + g) : tile;     // bit 3: every CTA rewrites its own two tiles (stores stay in L2)
+      char* act_tile = (MODE == MODE_FWD) ? a.act_img + img_tile * (int64_t)FWD_CHUNKS * CHUNK_BYTES : nullptr;
+      char* dy_tile = (MODE == MODE_BWD) ? a.dy_img + img_tile * (int64_t)BWD_CHUNKS * CHUNK_BYTES : nullptr;
       uint32_t* mask_tile = a.mask + tile * (int64_t)MASK_WORDS_PER_TILE;
       // every bulk store of the previous unit must have finished READING shared memory before it is rewritten
       if (tslot == 0 && !(skip & 4)) bulk_wait_read();
