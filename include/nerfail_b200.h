@@ -268,6 +268,14 @@ NFB_API int nfb_rgba_to_chw(const float* img_f32, const uint8_t* img_u8, const f
                             float fill, float* out, void* stream);
 NFB_API int nfb_chw_to_rgba(const float* g_out, const float* alpha_src, int64_t B, int64_t HW, float* g_img, void* stream);
 
+/* The I-FGSM update of attack_NeRFail_S.py:357-392 restricted to the rows it can change (alpha > 0; active_idx [n] int64 row
+ * numbers of the [T,4] perturbation table, fixed for a whole attack).  nfb_attack_pack_rgb packs the RGB gradient of those
+ * rows, [n,3], which is all a data-parallel attack has to all-reduce; nfb_attack_sign_step applies
+ * rgb <- clamp(rgb - signed_step * sign(g), init - eps, init + eps) to them in place (signed_step > 0 descends).     */
+NFB_API int nfb_attack_pack_rgb(const float* grad, const int64_t* active_idx, int64_t n, float* packed, void* stream);
+NFB_API int nfb_attack_sign_step(float* table, const float* init, const int64_t* active_idx, const float* packed_grad,
+                                 int64_t n, float signed_step, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

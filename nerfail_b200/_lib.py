@@ -48,6 +48,8 @@ SIGNATURES = {
     "nfb_render_rays_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
     "nfb_render_rays_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr] + [c_ptr] * 8
                             + [c_ptr, C.c_size_t, c_ptr]),
+    "nfb_attack_pack_rgb": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "nfb_attack_sign_step": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, C.c_float, C.c_float, c_ptr]),
     "nfb_rgba_to_chw": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr]),
     "nfb_chw_to_rgba": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "nfb_adam_step": (c_int, [c_ptr, c_int, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_ptr]),

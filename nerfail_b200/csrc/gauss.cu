@@ -252,6 +252,36 @@ chw_to_rgba_kernel(const float* __restrict__ g_out, const float4* __restrict__ a
 
 }  // namespace nfb
 
+namespace nfb {
+
+// The RGB columns of the active rows of grad_spatial_rgb, packed: out[k] = grad[idx[k]].xyz  (what the sign step consumes)
+__global__ void __launch_bounds__(256)
+attack_pack_rgb_kernel(const float4* __restrict__ grad, const int64_t* __restrict__ idx, int64_t n, float* __restrict__ out) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = __ldg(grad + __ldg(idx + k));
+    out[3 * k] = g.x; out[3 * k + 1] = g.y; out[3 * k + 2] = g.z;
+  }
+}
+
+// attack_NeRFail_S.py:357-392 on the active rows: rgb <- clamp(rgb -/+ step * sign(g), init - eps, init + eps)
+__global__ void __launch_bounds__(256)
+attack_sign_step_kernel(float4* __restrict__ table, const float4* __restrict__ init, const int64_t* __restrict__ idx,
+                        const float* __restrict__ g, int64_t n, float step, float eps) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = __ldg(idx + k);
+    float4 t = table[r];
+    const float4 t0 = __ldg(init + r);
+    const float gx = g[3 * k], gy = g[3 * k + 1], gz = g[3 * k + 2];
+    auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };     // torch.sign
+    t.x = fmaxf(fminf(t.x - step * sgn(gx), t0.x + eps), t0.x - eps);
+    t.y = fmaxf(fminf(t.y - step * sgn(gy), t0.y + eps), t0.y - eps);
+    t.z = fmaxf(fminf(t.z - step * sgn(gz), t0.z + eps), t0.z - eps);
+    table[r] = t;
+  }
+}
+
+}  // namespace nfb
+
 extern "C" {
 
 int nfb_gauss_weights(const float* dist_idx, int64_t B, int64_t HW, float c, float* i_w, void* stream) {
@@ -328,6 +358,24 @@ int nfb_chw_to_rgba(const float* g_out, const float* alpha_src, int64_t B, int64
   nfb::chw_to_rgba_kernel<<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
       g_out, reinterpret_cast<const float4*>(alpha_src), B, HW, reinterpret_cast<float4*>(g_img));
   return nfb::check_launch("chw_to_rgba");
+}
+
+int nfb_attack_pack_rgb(const float* grad, const int64_t* active_idx, int64_t n, float* packed, void* stream) {
+  NFB_REQUIRE(grad && active_idx && packed && n >= 0, "attack_pack_rgb: bad argument");
+  NFB_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "attack_pack_rgb: grad must be 16-byte aligned");
+  if (n == 0) return NFB_OK;
+  nfb::attack_pack_rgb_kernel<<<nfb::stream_grid(n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(grad), active_idx, n, packed);
+  return nfb::check_launch("attack_pack_rgb");
+}
+
+int nfb_attack_sign_step(float* table, const float* init, const int64_t* active_idx, const float* packed_grad, int64_t n,
+                         float signed_step, float eps, void* stream) {
+  NFB_REQUIRE(table && init && active_idx && packed_grad && n >= 0 && eps >= 0.f, "attack_sign_step: bad argument");
+  NFB_REQUIRE(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(init)) & 15) == 0, "attack_sign_step: tables must be 16-byte aligned");
+  if (n == 0) return NFB_OK;
+  nfb::attack_sign_step_kernel<<<nfb::stream_grid(n), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float4*>(table), reinterpret_cast<const float4*>(init), active_idx, packed_grad, n, signed_step, eps);
+  return nfb::check_launch("attack_sign_step");
 }
 
 }  // extern "C"

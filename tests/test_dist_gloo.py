@@ -33,6 +33,12 @@ def _worker(rank, world, port, out):
         want = init.clone()
         want[..., :3] = torch.clamp(init[..., :3] - 2.0 * torch.sign(full[..., :3]) * (init[..., 3:4] > 0), -3.0, 3.0)
         assert torch.allclose(s, want), "sign must be taken after the reduce"
+        # exchanging and updating only the active rows' RGB (what the update consumes) gives the same table
+        s2 = init.clone()
+        idx = nd.active_rows(s2)
+        assert idx.numel() == int((init[..., 3] > 0).sum())
+        s2 = nd.attack_sign_step_(s2, per_view[nd.shard_views(4, rank, world)].sum(0), init, step=2.0, eps=3.0, active_idx=idx)
+        assert torch.equal(s2, s)
         # data-parallel retraining: mean-of-ranks gradient equals the full-batch gradient
         torch.manual_seed(1)
         lin = torch.nn.Linear(7, 3)

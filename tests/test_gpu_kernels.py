@@ -275,6 +275,30 @@ def test_classifier_input_conversion_and_its_derivatives(cuda):
     assert torch.equal(ha.cpu(), hb)
 
 
+def test_attack_sign_step_on_active_rows_equals_full_table_update(cuda):
+    """dist.attack_sign_step_ (attack_NeRFail_S.py:357-392) with the active-row exchange (nfb_attack_pack_rgb +
+    nfb_attack_sign_step: only the RGB of rows with A > 0 is packed, reduced and updated) against the full-table torch
+    expression, descending and ascending, including rows at the clamp and zero gradients."""
+    from nerfail_b200 import dist as nd
+    g = torch.Generator().manual_seed(9)
+    P, H, W = 2, 17, 13
+    init = torch.randn(P, H, W, 4, generator=g) * 3
+    init[..., 3] = (torch.rand(P, H, W, generator=g) > 0.45).float() * 255
+    cur = init.clone()
+    cur[..., :3] += (torch.rand(P, H, W, 3, generator=g) - 0.5) * 6.0          # some rows sit at init +- eps already
+    cur[..., :3] = torch.max(torch.min(cur[..., :3], init[..., :3] + 2.5), init[..., :3] - 2.5)
+    grad = torch.randn(P, H, W, 4, generator=g)
+    grad[0, :3] = 0.0                                                          # sign(0) = 0: no step
+    for minimise in (True, False):
+        want = nd.attack_sign_step_(cur.clone(), grad.clone(), init, 2.0, 2.5, minimise=minimise)
+        s = cur.clone().to(cuda)
+        idx = nd.active_rows(s)
+        got = nd.attack_sign_step_(s, grad.clone().to(cuda), init.to(cuda), 2.0, 2.5, minimise=minimise, active_idx=idx)
+        assert torch.equal(got.cpu(), want)
+        packed = nd.allreduce_active_rgb(grad.to(cuda), idx)
+        assert torch.equal(packed.cpu(), grad.reshape(-1, 4)[idx.cpu(), :3])
+
+
 def test_knn8_bit_exact_indices(cuda):
     from nerfail_b200 import ops
     g = golden("knn.npz")
