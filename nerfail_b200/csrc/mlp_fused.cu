@@ -1020,13 +1020,29 @@ static int train_launch(int mode, const nfb_mlp_t* h, nfb::tr::TrainArgs& a, voi
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  const bool aux = a.skip != 0 || a.ready != nullptr;
+  static unsigned long long* wait_dbg = []() -> unsigned long long* {       // NERFAIL_B200_TRAIN_WAITS=1: wait-cycle counters
+    const char* e = getenv("NERFAIL_B200_TRAIN_WAITS");
+    if (!(e && e[0] == '1')) return nullptr;
+    unsigned long long* p = nullptr;
+    cudaMalloc(&p, 4 * sizeof(unsigned long long));
+    return p;
+  }();
+  a.wait_cycles = wait_dbg;
+  if (wait_dbg) cudaMemsetAsync(wait_dbg, 0, 4 * sizeof(unsigned long long), (cudaStream_t)stream);
+  const bool aux = a.skip != 0 || a.ready != nullptr || wait_dbg != nullptr;
   cudaError_t e = (mode == nfb::tr::MODE_FWD)
       ? (aux ? cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD, true>, a)
              : cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_FWD, false>, a))
       : (aux ? cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, true>, a)
              : cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, false>, a));
   if (e != cudaSuccess) return nfb::fail(NFB_E_CUDA, "mlp_train: cluster launch: %s", cudaGetErrorString(e));
+  if (wait_dbg) {
+    unsigned long long h[4];
+    cudaMemcpy(h, wait_dbg, sizeof h, cudaMemcpyDeviceToHost);
+    const double n = groups, T = (double)h[3];
+    fprintf(stderr, "%s waits (share of CTA 0's %.0f cycles): MMA warp A_READY %.1f %%, W_FULL %.1f %%; epilogue warp ACC_FULL %.1f %%\n",
+            mode == nfb::tr::MODE_FWD ? "train fwd" : "bwd data", T, 100.0 * h[0] / n / T, 100.0 * h[1] / n / T, 100.0 * h[2] / (2.0 * n) / T);
+  }
   return nfb::check_launch(mode == nfb::tr::MODE_FWD ? "mlp_fwd_train" : "mlp_bwd_data");
 }
 

@@ -36,6 +36,8 @@ struct TrainArgs {
   const MlpSide* side;
   int cslot;
   int* abort_flag;
+  unsigned long long* wait_cycles; // profiling only (AUX instantiation): [0] += cycles the MMA warps waited for A_READY, [1] for W_FULL,
+                                  // [2] += cycles the epilogue warps of slot 0 / quarter 0 waited for ACC_FULL, [3] += kernel cycles of CTA 0
   const float* rays;              // [R,11]           (MODE_FWD)
   const float* z_vals;            // [M]              (MODE_FWD)
   int64_t M;
@@ -169,6 +171,8 @@ mlp_train_kernel(const TrainArgs a) {
     if (leader) {
       // ================= MMA issuer =================
       uint32_t pos = 0, ready_phase0 = 0, ready_phase1 = 0;
+      long long w_a = 0, w_w = 0;
+      const long long t_begin = AUX ? clock64() : 0;
       for (int64_t unit = group; unit < nunits; unit += ngroups) {
         for (int s = 0; s < nsteps; ++s) {
           const int kch = kchunks(s), halves = halves_of(s);
@@ -177,7 +181,7 @@ mlp_train_kernel(const TrainArgs a) {
           const uint32_t p0 = pos;
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            mbar_wait(A_READY(g), g == 0 ? ready_phase0 : ready_phase1, abort_flag);
+            { const long long t0 = AUX ? clock64() : 0; mbar_wait(A_READY(g), g == 0 ? ready_phase0 : ready_phase1, abort_flag); if (AUX) w_a += clock64() - t0; }
             if (g == 0) ready_phase0 ^= 1; else ready_phase1 ^= 1;
             tc_fence_after();
             const uint32_t act = base + SM_ACT + g * 4 * CHUNK_BYTES, pe = base + SM_PE + g * CHUNK_BYTES;
@@ -185,7 +189,7 @@ mlp_train_kernel(const TrainArgs a) {
             for (int c = 0; c < main_ch; ++c) {
               const uint32_t p = p0 + c;
               const int stage = p & (NSTAGE - 1);
-              if (g == 0) { mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag); tc_fence_after(); }
+              if (g == 0) { const long long t0 = AUX ? clock64() : 0; mbar_wait(W_FULL(stage), (p >> 2) & 1, abort_flag); if (AUX) w_w += clock64() - t0; tc_fence_after(); }
               const uint64_t ad = desc_of(MODE == MODE_FWD ? a_chunk_addr(s, c, act, pe) : act + c * CHUNK_BYTES);
               const uint64_t bd = desc_of(base + SM_W + stage * CHUNK_BYTES);
               if (elect_one()) {
@@ -219,6 +223,11 @@ mlp_train_kernel(const TrainArgs a) {
           pos += kch;
         }
       }
+      if (AUX && a.wait_cycles && lane == 0) {
+        atomicAdd(a.wait_cycles, (unsigned long long)w_a);
+        atomicAdd(a.wait_cycles + 1, (unsigned long long)w_w);
+        if (blockIdx.x == 0) atomicAdd(a.wait_cycles + 3, (unsigned long long)(clock64() - t_begin));
+      }
     } else {
       uint32_t pos = 0;
       for (int64_t unit = group; unit < nunits; unit += ngroups)
@@ -244,6 +253,7 @@ mlp_train_kernel(const TrainArgs a) {
     const MlpSide* __restrict__ sd = &c_side[a.cslot];
     const MlpSide* __restrict__ sg = a.side;
     uint32_t full_phase = 0;
+    long long w_acc = 0;
     const int tslot = ((e & 7) << 5) + lane;
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" :: "r"(pair_bar) : "memory"); };
     auto slot_sync = [&]() { asm volatile("bar.sync %0, 256;" :: "r"(slot_bar) : "memory"); };
@@ -331,7 +341,7 @@ mlp_train_kernel(const TrainArgs a) {
 
       float sigma = 0.f;
       for (int s = 0; s < nsteps; ++s) {
-        mbar_wait(ACC_FULL(g), full_phase, abort_flag);
+        { const long long t0 = AUX ? clock64() : 0; mbar_wait(ACC_FULL(g), full_phase, abort_flag); if (AUX) w_acc += clock64() - t0; }
         full_phase ^= 1;
         tc_fence_after();
         const bool last = (s == nsteps - 1);
@@ -519,6 +529,7 @@ mlp_train_kernel(const TrainArgs a) {
       }
       prev_tile = tile;
     }
+    if (AUX && a.wait_cycles && e == 0 && lane == 0) atomicAdd(a.wait_cycles + 2, (unsigned long long)w_acc);
     if (tslot == 0) {
       bulk_wait_all();                                 // the images must be complete in HBM when the kernel ends
       if (AUX && MODE == MODE_BWD && ready && prev_tile >= 0) publish_ready(ready + prev_tile, 1 + BWD_STEPS);
