@@ -198,8 +198,8 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
             x, x_rgba = ops.gauss_gather_fwd(table.detach().reshape(-1, 4), w_idx[:nb_], ori[:nb_], 32.0)
             ops.gauss_scatter_bwd(None, gx[:nb_], x, w_idx[:nb_], ori[:nb_], 32.0, table.shape, out=grad)
             done += nb_; i += 1
-        # the whole table: at NVLink speed the 30.7 MB all-reduce (0.873 ms per iteration at 8 GPUs) beats packing the 9.2 MB
-        # the sign step consumes (dist.allreduce_active_rgb: 0.925 ms) - the exchange is latency-, not bandwidth-bound
+        # the whole table: at NVLink speed packing the 9.2 MB the sign step consumes (dist.allreduce_active_rgb: 0.93 ms per
+        # iteration at 8 GPUs) buys nothing over the 30.7 MB all-reduce (0.87-1.00 ms over three runs): latency-, not bandwidth-bound
         nd.allreduce_sum_(grad)
         return grad
 

@@ -93,7 +93,7 @@ def allreduce_active_rgb(grad: torch.Tensor, active_idx: torch.Tensor) -> torch.
     """The part of grad_spatial_rgb the update consumes — the RGB columns of the active rows — packed to [n_active, 3] and
     summed over ranks: 0.75 x (active fraction) of the 30.72 MB a full all-reduce would move (0.3 x for the ~40 % of
     pixels an object covers).  For links slower than NVLink: on an 8 x B200 NVSwitch node the exchange is latency-bound and
-    the full-table all-reduce is faster (0.873 vs 0.925 ms per 100-view iteration), so bench.py uses that."""
+    packing buys nothing (0.93 ms per 100-view iteration against 0.87-1.00 ms with the full table), so bench.py keeps the table."""
     if grad.is_cuda:
         from . import _lib
         g4 = grad.reshape(-1, 4)
