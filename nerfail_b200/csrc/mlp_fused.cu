@@ -750,6 +750,17 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
               }
             }
           }
+          if (s == 8 && hcol == 0) {                   // view-direction features into the (free) PE chunk
+            float f[64];
+            encode3<L_DIR>(vx, vy, vz, f);
+            store_row_chunk(pe, row, f);
+          }
+          // This warp's share of the next A operand is in shared memory: hand it over NOW.  What follows (the sigma
+          // combine, the refill of the bias row) touches neither the activation nor the encoding chunks the next MMA
+          // reads, so its three barriers run beside that MMA instead of delaying it.
+          if (tracing && e == 0) trace_evt(2, 0x6000 | (s << 4) | g, clock64(), clock64(), 2);
+          if (!last) signal_a_ready();
+          if (tracing && e == 0) trace_evt(2, 0x4000 | (s << 4) | g, clock64(), clock64(), 0);
           if (s == 7) {
             // combine the two column halves of sigma: the PE chunk is free between step 5 (last reader) and step 8
             if (hcol == 1) scratch_pe[row] = sig_acc;
@@ -757,18 +768,10 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             if (hcol == 0) sigma = sig_acc + scratch_pe[row] + sd->b_alpha;
             pair_sync();
           }
-          if (s == 8 && hcol == 0) {                   // view-direction features into the (free) PE chunk
-            float f[64];
-            encode3<L_DIR>(vx, vy, vz, f);
-            store_row_chunk(pe, row, f);
-          }
-          if (tracing && e == 0) trace_evt(2, 0x6000 | (s << 4) | g, clock64(), clock64(), 2);
           slot_sync();                                 // every warp of the slot has read this step's bias row
           bias_s[tslot] = next_bias;
           slot_sync();
           if (tracing && e == 0) trace_evt(2, 0x6800 | (s << 4) | g, clock64(), clock64(), 2);
-          if (!last) signal_a_ready();
-          if (tracing && e == 0) trace_evt(2, 0x4000 | (s << 4) | g, clock64(), clock64(), 0);
         } else {
           // ---- views layer epilogue: relu(acc + b) . w_rgb -> raw; this thread covers 64 of the 128 columns ----
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;

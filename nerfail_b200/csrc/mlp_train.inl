@@ -501,16 +501,19 @@ mlp_train_kernel(const TrainArgs a) {
                            pack_bf16(h[8 * u + 4], h[8 * u + 5]), pack_bf16(h[8 * u + 6], h[8 * u + 7]));
           }
         }
+        if (MODE == MODE_FWD && s == 8 && hcol == 0) {
+          float f[64];
+          encode3<L_DIR>(vx, vy, vz, f);
+          store_row_chunk(pe, row, f);
+        }
+        // this warp's share of the next A operand is complete: hand it to the MMA warp before the barriers that only
+        // serve the sigma combine, the image stores and the bias row (they then run beside the next MMA)
+        if (!last) signal_a_ready();
         if (MODE == MODE_FWD && s == 7) {
           if (hcol == 1) scratch_pe[row] = sig_acc;
           pair_sync();
           if (hcol == 0) sigma = sig_acc + scratch_pe[row] + sd->b_alpha;
           pair_sync();
-        }
-        if (MODE == MODE_FWD && s == 8 && hcol == 0) {
-          float f[64];
-          encode3<L_DIR>(vx, vy, vz, f);
-          store_row_chunk(pe, row, f);
         }
         fence_proxy_async();
         slot_sync();                                   // activation chunks (and the bias row) of this step are final
@@ -525,7 +528,6 @@ mlp_train_kernel(const TrainArgs a) {
         }
         if (MODE == MODE_FWD) bias_s[tslot] = next_bias;
         slot_sync();
-        if (!last) signal_a_ready();
       }
       prev_tile = tile;
     }
