@@ -750,23 +750,27 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
               }
             }
           }
-          if (s == 8 && hcol == 0) {                   // view-direction features into the (free) PE chunk
-            float f[64];
-            encode3<L_DIR>(vx, vy, vz, f);
-            store_row_chunk(pe, row, f);
-          }
           // This warp's share of the next A operand is in shared memory: hand it over NOW.  What follows (the sigma
-          // combine, the refill of the bias row) touches neither the activation nor the encoding chunks the next MMA
-          // reads, so its three barriers run beside that MMA instead of delaying it.
+          // combine, the view-direction encoding, the refill of the bias row) touches neither the activation chunks nor,
+          // before step 9, the encoding chunk the next MMA reads, so it runs beside that MMA instead of delaying it.
           if (tracing && e == 0) trace_evt(2, 0x6000 | (s << 4) | g, clock64(), clock64(), 2);
           if (!last) signal_a_ready();
           if (tracing && e == 0) trace_evt(2, 0x4000 | (s << 4) | g, clock64(), clock64(), 0);
           if (s == 7) {
-            // combine the two column halves of sigma: the PE chunk is free between step 5 (last reader) and step 8
-            if (hcol == 1) scratch_pe[row] = sig_acc;
+            // The encoding chunk is free from here (its last reader was the MMA of step 5) until step 9.  First the two
+            // column halves of sigma are combined through the row's own last padding columns (logical columns 62, 63),
+            // then the column-half-0 thread writes the view-direction features of its row over the whole row (the
+            // padding becomes zero again); the arrive at the end of step 8 orders these stores before step 9's MMA.
+            float* slot = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + SM_PE + g * CHUNK_BYTES +
+                                                   row * 128 + (((7 ^ (row & 7)) & 7) << 4) + 12);
+            if (hcol == 1) *slot = sig_acc;
             pair_sync();
-            if (hcol == 0) sigma = sig_acc + scratch_pe[row] + sd->b_alpha;
-            pair_sync();
+            if (hcol == 0) {
+              sigma = sig_acc + *slot + sd->b_alpha;
+              float f[64];
+              encode3<L_DIR>(vx, vy, vz, f);
+              store_row_chunk(pe, row, f);
+            }
           }
           slot_sync();                                 // every warp of the slot has read this step's bias row
           bias_s[tslot] = next_bias;
