@@ -87,9 +87,16 @@ NFB_API int64_t nfb_mlp_param_count(const nfb_mlp_t* h);
 NFB_API int nfb_mlp_fwd(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs,
                 const float* rays, const float* z_vals, int R, int S, float* raw, void* stream);
 
-/* 0 = healthy.  NFB_E_CUDA if a pipeline barrier inside the fused kernel timed out since the last call
- * (the kernel bails out instead of hanging the GPU; its outputs are then invalid).  Synchronises the device. */
+/* 0 = healthy.  NFB_E_CUDA if a pipeline barrier inside a fused kernel of this network timed out since the last call
+ * (the kernel bails out instead of hanging the GPU; its outputs are then invalid).  Synchronises the device and CLEARS
+ * the flag.  The flag lives in mapped pinned host memory, so it is also visible without a synchronisation:
+ *   - nfb_mlp_poll reads it (no sync, no clear): NFB_E_CUDA once a kernel that has already run timed out;
+ *   - every launch entry point of the network (nfb_mlp_fwd, nfb_mlp_fwd_train, nfb_mlp_bwd_*, nfb_render_rays_fwd) polls it
+ *     first and refuses to run (NFB_E_CUDA) while it is raised, so one time-out cannot silently poison later results.
+ * Any number of networks may be alive per device; the 4 constant-memory entries that hold their head weights are shared
+ * LRU (a network that lost its entry re-acquires one at its next launch; that costs one host-side wait). */
 NFB_API int nfb_mlp_status(nfb_mlp_t* h);
+NFB_API int nfb_mlp_poll(const nfb_mlp_t* h);
 /* Validation entry: run only the first nsteps (1..10) MMA steps of the fused kernel and dump the fp32
  * post-activation values of the last executed step to dbg [R*S,256] (128 columns for the view layer).     */
 NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs,
@@ -252,7 +259,10 @@ NFB_API int nfb_gauss_weights(const float* dist_idx, int64_t B, int64_t HW, floa
 NFB_API int nfb_gauss_gather_fwd(const float* table, int64_t T, const float* w_idx, const uint8_t* ori,
                          int64_t B, int64_t HW, float eps, float* x, float* x_rgba, float* minmax,
                          void* stream);
-/* Backward of the above w.r.t. table: warp-aggregated red.global.add.v4.f32 scatter.
+/* Backward of the above w.r.t. table: one red.global.add.v4.f32 per (pixel, neighbour) straight into the L2-resident
+ * table.  (north_star asks for warp-aggregated atomics; the match.any merge of equal rows was built and measured SLOWER
+ * on B200 — 64-73 us against 42-47 us per 800x800 view, the L2 atomic units absorb duplicates faster than eight
+ * match.any rounds per pixel remove them — so it is opt-in, NERFAIL_B200_SCATTER_AGG=1; csrc/gauss.cu.)
  * g_x, g_xrgba [B,HW,4] (either may be NULL); x is the saved forward output; g_table [T,4] is
  * ACCUMULATED into (caller zeroes it).                                                               */
 NFB_API int nfb_gauss_scatter_bwd(const float* g_x, const float* g_xrgba, const float* x, const float* w_idx,

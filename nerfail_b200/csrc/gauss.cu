@@ -1,4 +1,5 @@
-// GaussNet: Gaussian weights, 8-neighbour weighted gather (forward) and warp-aggregated scatter (backward).
+// GaussNet: Gaussian weights, 8-neighbour weighted gather (forward) and L2-reduction scatter (backward; per-lane
+// red.global.add.v4.f32 by default, warp-aggregated variant opt-in because it measured slower — see the launcher).
 //
 // Reference arithmetic: model/GaussNet.py:169-186 (create_gauss_w.forward), :53-119 (gauss_net.forward up
 // to x_rgba).  HBM/L2-bound: 228 B/pixel each way; the 30.7 MB [P*H*W,4] table is L2

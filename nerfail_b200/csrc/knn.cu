@@ -5,7 +5,7 @@
 // reference's cdist runs in matmul mode, whose fp32 cancellation makes its own ordering noisy
 // (SURVEY.md §0.4); this kernel computes the direct-difference squared distance
 //     d2 = ((dx*dx + dy*dy) + dz*dz)          (fp32, round-to-nearest, no FMA contraction)
-// orders by (d2, candidate index) and returns sqrt(d2), which is what oracle/knn_oracle.py pins bit-exactly.
+// orders by (d2, candidate index) and returns sqrt(d2), which is what oracle/gauss_oracle.py:knn8_exact pins bit-exactly.
 //
 // Layout: one thread owns QPT queries and keeps their top-8 (d2, idx) sorted in registers; candidates stream
 // through shared memory in tiles (every lane reads the same candidate -> LDS.128 broadcast).  Compute-bound

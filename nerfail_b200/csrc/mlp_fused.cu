@@ -72,7 +72,8 @@ struct MlpSide {
 
 // The epilogues read biases / head weights warp-uniformly.  With ~225 KB of shared memory per CTA the L1 carve-out is
 // a few KB, so global loads of these 12 KB per network miss L1 and cost an L2 round trip per 32 columns (measured: 900
-// cycles per 32-column epilogue iteration).  They live in constant memory instead: up to MAX_NETS networks per device.
+// cycles per 32-column epilogue iteration).  They live in constant memory instead: MAX_NETS entries per device, shared
+// LRU among however many networks are alive (ensure_cslot below).
 constexpr int MAX_NETS = 4;
 __constant__ MlpSide c_side[MAX_NETS];
 
@@ -82,8 +83,9 @@ struct nfb_mlp {
   __nv_bfloat16* image;      // TOTAL_BLOCKS x 16 KB pre-swizzled weight blocks
   __nv_bfloat16* image_t;    // transposed blocks for the data-gradient chain (68 x 16 KB)
   nfb::MlpSide* side;        // staging copy in global memory (written by the pack kernel)
-  int cslot;                 // index into the __constant__ c_side table of this device
-  int* abort_flag;           // set by the kernel if a barrier wait timed out
+  mutable int cslot;         // index into the __constant__ c_side table of this device, or -1 while evicted (see ensure_cslot)
+  int* abort_flag;           // set by the kernel if a barrier wait timed out: DEVICE alias of abort_host (mapped pinned memory)
+  volatile int* abort_host;  // the same word seen from the host: polled without synchronising (nfb_mlp_poll, every launch)
   void* zero16k;             // 16 KB of zeros: the padding dY chunk of the head weight-gradient products
   cudaStream_t side_stream;  // second stream + fork/join events: the weight-gradient kernel of nfb_mlp_bwd runs next to
   cudaEvent_t ev_fork, ev_join;   // the data-gradient kernel on its own SMs
@@ -842,17 +844,82 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
 // C ABI
 // ---------------------------------------------------------------------------------------------------
 namespace {
+// The head weights / biases of a network are read through constant memory (c_side, MAX_NETS entries per device).  More
+// networks than entries may be alive: a network without an entry takes the least recently used one at its next launch
+// (the evicted network re-acquires one the same way).  An eviction first waits, on the host, for the last kernel that read
+// the victim's entry; entries referenced by a CUDA graph capture are never evicted.
+struct SideSlot {
+  const nfb_mlp* owner = nullptr;
+  cudaEvent_t last_use = nullptr;
+  bool event_valid = false;     // last_use was recorded after the owner's latest launch
+  bool pinned = false;          // used inside a stream capture: the graph replays with this entry, keep it
+  uint64_t tick = 0;
+};
 std::mutex g_slot_mutex;
-unsigned g_slot_used[64] = {0};      // per device: bitmap of c_side entries in use
-int acquire_cslot(int device) {
-  std::lock_guard<std::mutex> lock(g_slot_mutex);
+SideSlot g_slots[64][nfb::MAX_NETS];
+int g_alive[64] = {0};
+uint64_t g_tick = 0;
+
+int try_free_cslot(int device, const nfb_mlp* h) {
   for (int i = 0; i < nfb::MAX_NETS; ++i)
-    if (!(g_slot_used[device] & (1u << i))) { g_slot_used[device] |= 1u << i; return i; }
+    if (!g_slots[device][i].owner) {
+      g_slots[device][i].owner = h; g_slots[device][i].event_valid = false; g_slots[device][i].pinned = false;
+      g_slots[device][i].tick = ++g_tick;
+      return i;
+    }
   return -1;
 }
 void release_cslot(int device, int slot) {
+  if (slot >= 0) { g_slots[device][slot].owner = nullptr; g_slots[device][slot].pinned = false; g_slots[device][slot].event_valid = false; }
+}
+bool is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return st != cudaStreamCaptureStatusNone;
+}
+// Makes sure h owns a constant-memory entry holding its side parameters before a kernel of h is launched on `stream`.
+int ensure_cslot(const nfb_mlp* h, cudaStream_t stream) {
   std::lock_guard<std::mutex> lock(g_slot_mutex);
-  if (slot >= 0) g_slot_used[device] &= ~(1u << slot);
+  const int dev = h->device;
+  if (h->cslot >= 0) { g_slots[dev][h->cslot].tick = ++g_tick; return NFB_OK; }
+  int slot = try_free_cslot(dev, h);
+  if (slot < 0) {
+    int victim = -1;
+    for (int i = 0; i < nfb::MAX_NETS; ++i)
+      if (!g_slots[dev][i].pinned && (victim < 0 || g_slots[dev][i].tick < g_slots[dev][victim].tick)) victim = i;
+    if (victim < 0)
+      return nfb::fail(NFB_E_UNSUPPORTED, "mlp: all %d constant-memory entries are referenced by captured CUDA graphs; destroy a network first", nfb::MAX_NETS);
+    if (is_capturing(stream))
+      return nfb::fail(NFB_E_UNSUPPORTED, "mlp: more than %d fused networks alive: launch this network once outside the stream capture first", nfb::MAX_NETS);
+    SideSlot& v = g_slots[dev][victim];
+    cudaError_t e = v.event_valid ? cudaEventSynchronize(v.last_use) : cudaDeviceSynchronize();
+    if (e != cudaSuccess) return nfb::fail(NFB_E_CUDA, "mlp: waiting for the evicted network: %s", cudaGetErrorString(e));
+    v.owner->cslot = -1;
+    v.owner = h; v.event_valid = false; v.tick = ++g_tick;
+    slot = victim;
+  }
+  h->cslot = slot;
+  NFB_CUDA(cudaMemcpyToSymbolAsync(nfb::c_side, h->side, sizeof(nfb::MlpSide), (size_t)slot * sizeof(nfb::MlpSide),
+                                   cudaMemcpyDeviceToDevice, stream));
+  return NFB_OK;
+}
+// After a launch of h on `stream`: remember when its entry was last read (only needed once entries are contended).
+void note_cslot_use(const nfb_mlp* h, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_slot_mutex);
+  if (h->cslot < 0) return;
+  SideSlot& s = g_slots[h->device][h->cslot];
+  if (is_capturing(stream)) { s.pinned = true; return; }
+  if (g_alive[h->device] <= nfb::MAX_NETS) { s.event_valid = false; return; }
+  if (!s.last_use && cudaEventCreateWithFlags(&s.last_use, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); s.last_use = nullptr; return; }
+  s.event_valid = cudaEventRecord(s.last_use, stream) == cudaSuccess;
+}
+// A barrier time-out of an earlier launch of this network leaves its flag raised (sticky until nfb_mlp_status clears it):
+// refuse to run on top of garbage.
+int refuse_if_aborted(const nfb_mlp* h, const char* what) {
+  if (h->abort_host && *h->abort_host)
+    return nfb::fail(NFB_E_CUDA, "%s: an earlier launch of this network hit a pipeline-barrier time-out (its outputs are invalid); "
+                                 "nfb_mlp_status() reports and clears it", what);
+  return NFB_OK;
 }
 }  // namespace
 
@@ -865,23 +932,21 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
                      "mlp_create: fused kernel is built for D=8 W=256 input_ch=63 input_ch_views=27 skips=[4] "
                      "(got D=%d W=%d input_ch=%d input_ch_views=%d skip=%d)", D, W, input_ch, input_ch_views, skip);
   nfb_mlp* h = new nfb_mlp();
-  h->image = nullptr; h->image_t = nullptr; h->side = nullptr; h->abort_flag = nullptr; h->zero16k = nullptr; h->cslot = -1;
+  h->image = nullptr; h->image_t = nullptr; h->side = nullptr; h->abort_flag = nullptr; h->abort_host = nullptr; h->zero16k = nullptr; h->cslot = -1;
   h->side_stream = nullptr; h->ev_fork = nullptr; h->ev_join = nullptr;
   h->n_params = nfb::param_layout().total;
   cudaError_t e = cudaGetDevice(&h->device);
   if (e == cudaSuccess && (h->device < 0 || h->device >= 64)) { delete h; return nfb::fail(NFB_E_UNSUPPORTED, "mlp_create: device index out of range"); }
-  if (e == cudaSuccess) {
-    h->cslot = acquire_cslot(h->device);
-    if (h->cslot < 0) {
-      delete h;
-      return nfb::fail(NFB_E_UNSUPPORTED, "mlp_create: at most %d fused networks per device may be alive at once", nfb::MAX_NETS);
-    }
+  if (e == cudaSuccess) {     // no free constant-memory entry is not an error: the first launch evicts the LRU one
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    h->cslot = try_free_cslot(h->device, h);
+    ++g_alive[h->device];
   }
   if (e == cudaSuccess) e = cudaMalloc(&h->image, (size_t)nfb::TOTAL_BLOCKS * nfb::CHUNK_BYTES);
   if (e == cudaSuccess) e = cudaMalloc(&h->image_t, (size_t)nfb::tr::TOTAL_BLOCKS_T * nfb::CHUNK_BYTES);
   if (e == cudaSuccess) e = cudaMalloc(&h->side, sizeof(nfb::MlpSide));
-  if (e == cudaSuccess) e = cudaMalloc(&h->abort_flag, sizeof(int));
-  if (e == cudaSuccess) e = cudaMemset(h->abort_flag, 0, sizeof(int));
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->abort_host, sizeof(int), cudaHostAllocMapped);
+  if (e == cudaSuccess) { *h->abort_host = 0; e = cudaHostGetDevicePointer((void**)&h->abort_flag, (void*)h->abort_host, 0); }
   if (e == cudaSuccess) e = cudaMalloc(&h->zero16k, nfb::CHUNK_BYTES);
   if (e == cudaSuccess) e = cudaMemset(h->zero16k, 0, nfb::CHUNK_BYTES);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
@@ -904,11 +969,16 @@ int nfb_mlp_create(nfb_mlp_t** out, int D, int W, int input_ch, int input_ch_vie
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nfb::SMEM_BYTES);
   if (e != cudaSuccess) {
-    cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag); cudaFree(h->zero16k);
+    cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->zero16k);
+    if (h->abort_host) cudaFreeHost((void*)h->abort_host);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
-    release_cslot(h->device, h->cslot);
+    if (h->device >= 0 && h->device < 64) {
+      std::lock_guard<std::mutex> lock(g_slot_mutex);
+      release_cslot(h->device, h->cslot);
+      --g_alive[h->device];
+    }
     delete h;
     return nfb::fail(NFB_E_CUDA, "mlp_create: %s", cudaGetErrorString(e));
   }
@@ -927,19 +997,27 @@ int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* st
   nfb::tr::pack_weights_T_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image_t);
   rc = nfb::check_launch("mlp_update.transposed");
   if (rc) return rc;
-  // stream-ordered device-to-device copy of the fp32 side parameters into this network's constant-memory entry
-  NFB_CUDA(cudaMemcpyToSymbolAsync(nfb::c_side, h->side, sizeof(nfb::MlpSide), (size_t)h->cslot * sizeof(nfb::MlpSide),
-                                   cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  // stream-ordered device-to-device copy of the fp32 side parameters into this network's constant-memory entry (a network
+  // that holds none right now copies them when it acquires one, ensure_cslot)
+  std::lock_guard<std::mutex> lock(g_slot_mutex);
+  if (h->cslot >= 0)
+    NFB_CUDA(cudaMemcpyToSymbolAsync(nfb::c_side, h->side, sizeof(nfb::MlpSide), (size_t)h->cslot * sizeof(nfb::MlpSide),
+                                     cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return NFB_OK;
 }
 
 int nfb_mlp_destroy(nfb_mlp_t* h) {
   if (!h) return NFB_OK;
-  cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->abort_flag); cudaFree(h->zero16k);
+  cudaFree(h->image); cudaFree(h->image_t); cudaFree(h->side); cudaFree(h->zero16k);
+  if (h->abort_host) cudaFreeHost((void*)h->abort_host);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
-  release_cslot(h->device, h->cslot);
+  {
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    release_cslot(h->device, h->cslot);
+    --g_alive[h->device];
+  }
   delete h;
   return NFB_OK;
 }
@@ -947,13 +1025,19 @@ int nfb_mlp_destroy(nfb_mlp_t* h) {
 // 0 = healthy; 1 = a barrier wait inside the fused kernel timed out (results invalid).  Synchronises the device.
 int nfb_mlp_status(nfb_mlp_t* h) {
   NFB_REQUIRE(h, "mlp_status: null handle");
-  int flag = 0;
-  NFB_CUDA(cudaMemcpy(&flag, h->abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
-  if (flag) {
-    cudaMemset(h->abort_flag, 0, sizeof(int));
+  NFB_CUDA(cudaDeviceSynchronize());
+  if (*h->abort_host) {
+    *h->abort_host = 0;
     return nfb::fail(NFB_E_CUDA, "mlp_fwd: pipeline barrier timed out inside the fused kernel");
   }
   return NFB_OK;
+}
+
+// The same flag WITHOUT synchronising or clearing: what the kernels that have finished so far reported.  Costs one read of
+// pinned host memory, so product paths poll it at their natural hand-over points (a finished view, optimizer.step).
+int nfb_mlp_poll(const nfb_mlp_t* h) {
+  NFB_REQUIRE(h, "mlp_poll: null handle");
+  return refuse_if_aborted(h, "mlp_poll");
 }
 
 static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs, const float* rays,
@@ -965,6 +1049,9 @@ static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const floa
   NFB_REQUIRE((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "mlp_fwd: raw must be 16-byte aligned");
   NFB_REQUIRE(nsteps >= 1 && nsteps <= nfb::NSTEP && (nsteps == nfb::NSTEP || dbg), "mlp_fwd: bad nsteps");
   if (R == 0) return NFB_OK;
+  int rc0 = refuse_if_aborted(h, "mlp_fwd");
+  if (rc0 == NFB_OK) rc0 = ensure_cslot(h, (cudaStream_t)stream);
+  if (rc0 != NFB_OK) return rc0;
   nfb::FwdArgs a;
   a.image = h->image; a.side = h->side; a.cslot = h->cslot; a.abort_flag = h->abort_flag;
   a.mode = mode; a.pts = pts; a.dirs = dirs; a.rays = rays; a.z_vals = z_vals;
@@ -993,6 +1080,7 @@ static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const floa
                         : cudaLaunchKernelEx(&cfg, nfb::mlp_fused_fwd_kernel<2, false>, a);
     if (e != cudaSuccess) return nfb::fail(NFB_E_CUDA, "mlp_fwd: cluster launch: %s", cudaGetErrorString(e));
   }
+  note_cslot_use(h, (cudaStream_t)stream);
   return nfb::check_launch("mlp_fwd");
 }
 
@@ -1013,6 +1101,10 @@ int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const floa
 static int train_launch(int mode, const nfb_mlp_t* h, nfb::tr::TrainArgs& a, void* stream, int max_groups = 0) {
   static const int skip = []() { const char* e = getenv("NERFAIL_B200_TRAIN_SKIP"); return e ? atoi(e) : 0; }();
   a.skip = skip;
+  int rc0 = refuse_if_aborted(h, mode == nfb::tr::MODE_FWD ? "mlp_fwd_train" : "mlp_bwd_data");
+  if (rc0 == NFB_OK) rc0 = ensure_cslot(h, (cudaStream_t)stream);
+  if (rc0 != NFB_OK) return rc0;
+  a.cslot = h->cslot;
   const int64_t rows_per_unit = 2 * nfb::TILE_M * 2;
   const int64_t nunits = (a.M + rows_per_unit - 1) / rows_per_unit;
   int groups = nfb::sm_count() / 2;
@@ -1043,6 +1135,7 @@ static int train_launch(int mode, const nfb_mlp_t* h, nfb::tr::TrainArgs& a, voi
       : (aux ? cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, true>, a)
              : cudaLaunchKernelEx(&cfg, nfb::tr::mlp_train_kernel<nfb::tr::MODE_BWD, false>, a));
   if (e != cudaSuccess) return nfb::fail(NFB_E_CUDA, "mlp_train: cluster launch: %s", cudaGetErrorString(e));
+  note_cslot_use(h, (cudaStream_t)stream);
   if (wait_dbg) {
     unsigned long long h[4];
     cudaMemcpy(h, wait_dbg, sizeof h, cudaMemcpyDeviceToHost);
@@ -1129,6 +1222,8 @@ int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const void* dy_
   nfb::WgradJob jobs[16];
   signed char need[16];
   const int n = wgrad_jobs(act_img, dy_img, grad, jobs, need);
+  const int rc0 = refuse_if_aborted(h, "mlp_bwd_weights");
+  if (rc0 != NFB_OK) return rc0;
   return nfb::launch_wgrad_grouped(jobs, n, ntiles, h->zero16k, h->abort_flag, stream, "mlp_bwd_weights", nullptr, nullptr, 0, g_raw, M);
 }
 

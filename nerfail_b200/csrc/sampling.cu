@@ -327,8 +327,12 @@ int nfb_sample_pdf(const float* bins, const float* weights, int w_pitch, const f
   NFB_REQUIRE(R >= 0 && nb >= 2 && N > 0 && w_pitch >= nb - 1, "sample_pdf: R=%d nb=%d N=%d w_pitch=%d", R, nb, N, w_pitch);
   if (nb > 2048) return nfb::fail(NFB_E_UNSUPPORTED, "sample_pdf: %d bins > 2048", nb);
   if (R == 0) return NFB_OK;
-  const size_t smem = (size_t)4 * 2 * nb * sizeof(float);
-  nfb::sample_pdf_kernel<<<nfb::grid_for(R, 4, 16), 128, smem, (cudaStream_t)stream>>>(
+  // a block keeps (cdf, bins) of one ray per warp: 4 warps while that fits the default 48 KB window, fewer above (nb <= 2048
+  // always fits with one warp: 16 KB)
+  int warps = 4;
+  while (warps > 1 && (size_t)warps * 2 * nb * sizeof(float) > 48 * 1024) warps >>= 1;
+  const size_t smem = (size_t)warps * 2 * nb * sizeof(float);
+  nfb::sample_pdf_kernel<<<nfb::grid_for(R, warps, 16), 32 * warps, smem, (cudaStream_t)stream>>>(
       bins, weights, w_pitch, u, R, nb, N, samples, inds);
   return nfb::check_launch("sample_pdf");
 }

@@ -40,6 +40,19 @@ def allreduce_sum_(t: torch.Tensor, async_op: bool = False):
     return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)
 
 
+def broadcast_params_(modules, src: int = 0) -> None:
+    """Initial parameter sync of data-parallel retraining: every rank takes rank `src`'s weights.  The broadcast writes
+    through `p.data`, which does not bump the version counters NeRF.fused() watches, so the packed bf16 images are
+    invalidated explicitly (NeRF.invalidate_fused)."""
+    if world()[1] > 1:
+        for m in modules:
+            for p in m.parameters():
+                dist.broadcast(p.data, src)
+    for m in modules:
+        if hasattr(m, "invalidate_fused"):
+            m.invalidate_fused()
+
+
 def _flat_view(grads):
     """The gradients as ONE tensor without a copy, if they are back-to-back views of one buffer (what the fused training
     backward hands to autograd: nfb_mlp_bwd_weights accumulates into a flat [n_params] gradient in state_dict order)."""

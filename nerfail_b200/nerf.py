@@ -34,12 +34,24 @@ class Embedder:
         self.out_dim = 3 + 6 * self.multires
 
     def embed(self, inputs: torch.Tensor, out: torch.Tensor | None = None, col0: int = 0, row_repeat: int = 1):
+        """Writes the encoding of inputs [..., 3] into out[:, col0:col0+out_dim] (a fresh [M, out_dim] tensor when out is
+        None).  Writing into a caller's buffer bypasses autograd, so it is refused for inputs that require grad: use
+        __call__ / embed_grad, which are differentiable w.r.t. the inputs like the reference's torch Embedder."""
         x = inputs.reshape(-1, 3)
+        if x.requires_grad and torch.is_grad_enabled():
+            if out is not None:
+                raise RuntimeError("nerfail_b200.Embedder.embed(out=...) is not differentiable w.r.t. its inputs; "
+                                   "call the embedder (or embed_grad) to keep the gradient to points / rays")
+            return ops.EmbedFn.apply(x, self.multires, row_repeat)
         if out is None:
             out = torch.empty((x.shape[0] * row_repeat, self.out_dim), dtype=torch.float32, device=x.device)
             col0 = 0
         ops.embed(x, self.multires, out, col0, row_repeat)
         return out
+
+    def embed_grad(self, inputs: torch.Tensor, row_repeat: int = 1):
+        """[M * row_repeat, out_dim] with autograd to the inputs (row i of the input fills rows i*row_repeat ...)."""
+        return ops.EmbedFn.apply(inputs.reshape(-1, 3), self.multires, row_repeat)
 
     def __call__(self, inputs: torch.Tensor):
         lead = inputs.shape[:-1]
@@ -134,6 +146,18 @@ class NeRF(nn.Module):
     def forward_rays_train(self, rays, z_vals):
         """raw [R,S,4] with autograd through the bf16 tensor-core training kernels (rays [R,11], z_vals [R,S])."""
         return ops.FusedMLPTrainFn.apply(self, rays, z_vals, *self.ordered_params())
+
+    def invalidate_fused(self) -> None:
+        """Forces the next fused() call to re-pack the bf16 weight image.  fused() notices optimizer steps and
+        load_state_dict through the parameters' version counters; writes that bypass them — `p.data.copy_()`,
+        `dist.broadcast(p.data, 0)`, EMA through `.data`, a raw-pointer kernel — do not bump the counter, so call this
+        after any such write (nerfail_b200.dist.broadcast_params_ and GraphedTrainStep do)."""
+        self._fused_version = None
+
+    def close(self) -> None:
+        """Releases the packed handle (device memory + its constant-memory entry) now instead of at garbage collection."""
+        self._fused = None
+        self._fused_version = None
 
     def _param_version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())

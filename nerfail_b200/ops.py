@@ -228,7 +228,14 @@ class FusedMLP:
         return self._run(1, None, None, rays, z_vals, R, S, **kw)
 
     def status(self) -> None:
+        """Synchronises the device; raises if a pipeline barrier of this network's kernels timed out, and clears the flag."""
         check(_lib.load().nfb_mlp_status(self._h), "nfb_mlp_status")
+
+    def poll(self) -> None:
+        """The same check without synchronising (one read of pinned host memory): raises once a kernel that has already
+        finished reported a time-out.  render_path's view sink, train_step and GraphedTrainStep call it at their hand-over
+        points; every launch of the network polls too and refuses to run on top of invalid results."""
+        check(_lib.load().nfb_mlp_poll(self._h), "nfb_mlp_poll")
 
     def __del__(self):
         try:
@@ -250,6 +257,36 @@ def embed(x: torch.Tensor, L: int, out: torch.Tensor, col0: int, row_repeat: int
     assert x.shape[0] * row_repeat == M
     with torch.cuda.device(out.device):
         check(_lib.load().nfb_embed(ptr(x), M, L, ptr(out), out.shape[1], col0, row_repeat, stream()), "nfb_embed")
+
+
+class EmbedFn(torch.autograd.Function):
+    """Positional encoding with the gradient to its input (run_nerf_helpers.py:36-50 is differentiable in the reference):
+    d/dx [x, sin(2^l x), cos(2^l x)]_l = g_x + sum_l 2^l (cos_l * g_sin_l - sin_l * g_cos_l), with sin_l / cos_l read back
+    from the saved output.  Only pose / ray optimisation built on the drop-in names needs it; no NeRFail path does, so
+    the backward is a handful of torch ops rather than a kernel."""
+
+    @staticmethod
+    def forward(ctx, x, L, row_repeat):
+        x = _f32(x)
+        out = torch.empty((x.shape[0] * row_repeat, 3 + 6 * L), dtype=torch.float32, device=x.device)
+        embed(x, L, out, 0, row_repeat)
+        ctx.save_for_backward(out)
+        ctx.L, ctx.row_repeat, ctx.n = L, row_repeat, x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        L = ctx.L
+        g = _f32(g)
+        gx = g[:, 0:3].clone()
+        sc = out[:, 3:].reshape(-1, L, 2, 3)
+        gg = g[:, 3:].reshape(-1, L, 2, 3)
+        freq = (2.0 ** torch.arange(L, device=g.device, dtype=torch.float32)).reshape(1, L, 1)
+        gx += (freq * (sc[:, :, 1] * gg[:, :, 0] - sc[:, :, 0] * gg[:, :, 1])).sum(1)
+        if ctx.row_repeat > 1:
+            gx = gx.reshape(ctx.n, ctx.row_repeat, 3).sum(1)
+        return gx, None, None
 
 
 def _view2d(t: torch.Tensor):
@@ -500,7 +537,8 @@ class _GaussScatterFn(torch.autograd.Function):
 
 
 class GaussGatherFn(torch.autograd.Function):
-    """(x, x_rgba) = gather/composite of model/GaussNet.py:53-119; backward = warp-aggregated scatter."""
+    """(x, x_rgba) = gather/composite of model/GaussNet.py:53-119; backward = one red.global.add.v4.f32 per (pixel, neighbour)
+    into the L2-resident table (the warp-aggregated variant measured slower on B200 and is opt-in, csrc/gauss.cu)."""
 
     @staticmethod
     def forward(ctx, spatial_rgb, w_idx, ori_u8, eps, minmax):

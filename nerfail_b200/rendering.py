@@ -48,7 +48,14 @@ def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64
         return fn.fused().forward_points(inputs, viewdirs)
     S = inputs.shape[-2] if inputs.dim() >= 2 else 1
     flat = inputs.reshape(-1, inputs.shape[-1])
-    if isinstance(embed_fn, nerf.Embedder):
+    wants_input_grad = torch.is_grad_enabled() and (flat.requires_grad or (viewdirs is not None and viewdirs.requires_grad))
+    if isinstance(embed_fn, nerf.Embedder) and wants_input_grad:
+        # pose / ray optimisation on the drop-in names: keep the gradient to the points and directions like the
+        # reference's torch Embedder (ops.EmbedFn), at the price of a concat
+        embedded = embed_fn.embed_grad(flat)
+        if viewdirs is not None:
+            embedded = torch.cat([embedded, embeddirs_fn.embed_grad(viewdirs.reshape(-1, 3), row_repeat=S)], -1)
+    elif isinstance(embed_fn, nerf.Embedder):
         width = embed_fn.out_dim + (embeddirs_fn.out_dim if viewdirs is not None else 0)
         embedded = torch.empty((flat.shape[0], width), dtype=torch.float32, device=flat.device)
         embed_fn.embed(flat, embedded, 0)
@@ -174,7 +181,13 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             else:
                 u = torch.rand((N_rays, N_importance), device=ray_batch.device)
         # z_mid, sample_pdf(weights[...,1:-1]), detach, sort(cat) and z_std in one kernel (:392-396, :412)
-        z_vals, z_samples, z_std = ops.hierarchical(z_vals, weights.detach(), N_importance, u)
+        if 3 <= N_samples <= 128 and N_samples + N_importance <= 512:
+            z_vals, z_samples, z_std = ops.hierarchical(z_vals, weights.detach(), N_importance, u)
+        else:       # outside the fused kernel's shapes: the reference's own sequence (:392-396, :412) on the sample_pdf kernel
+            z_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+            z_samples = ops.sample_pdf(z_mid, weights.detach()[..., 1:-1].contiguous(), N_importance, u)
+            z_std = torch.std(z_samples, dim=-1, unbiased=False)
+            z_vals, _ = torch.sort(torch.cat([z_vals, z_samples], -1), -1)
         run_fn = network_fn if network_fine is None else network_fine
         raw = query(z_vals, run_fn)
         rgb_map, disp_map, acc_map, weights, depth_map, pts_max = composite(raw, z_vals, with_pts_max)
@@ -265,10 +278,11 @@ class _ViewSink:
     buffers on a side stream, PNG / .npy encoding on a writer thread (cv2 and numpy release the GIL).  The reference
     does `.cpu().numpy()` + imageio.imwrite inline per view (run_nerf.py:155-169, nerf_to_coord.py:155-173)."""
 
-    def __init__(self, n_views, H, W, with_pts, savedir, device, depth=3):
+    def __init__(self, n_views, H, W, with_pts, savedir, device, depth=3, nets=()):
         import queue
         import threading
         self.savedir, self.with_pts = savedir, with_pts
+        self.nets = [n for n in nets if isinstance(n, NeRF)]      # polled for a barrier time-out once per finished view
         self.rgbs = np.empty((n_views, H, W, 3), np.float32)
         self.disps = np.empty((n_views, H, W), np.float32)
         self.pts = np.empty((n_views, H, W, 3), np.float32) if with_pts else None
@@ -306,6 +320,9 @@ class _ViewSink:
             k, name, sl, done, _keep = job
             try:
                 done.synchronize()
+                for n in self.nets:                                    # the view's kernels have finished: one host read each
+                    if n._fused is not None:
+                        n._fused.poll()
                 self.rgbs[k] = sl["rgb"].numpy()
                 self.disps[k] = sl["disp"].numpy()
                 if self.with_pts:
@@ -345,7 +362,8 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedi
             out = render(H, W, K, chunk=chunk, c2w=c2w[:3, :4], with_pts_max=with_pts_max, **render_kwargs)
             if sink is None:
                 dev = out[0].device
-                sink = _ViewSink(n, H, W, with_pts_max, savedir, dev)
+                sink = _ViewSink(n, H, W, with_pts_max, savedir, dev,
+                                 nets=(render_kwargs.get("network_fn"), render_kwargs.get("network_fine")))
             sink.put(k, '{:03d}'.format(ids[k]), out[0], out[1], out[3] if with_pts_max else None)
             if DEBUG:
                 print(k, time.time() - t0)

@@ -75,6 +75,15 @@ def _psnr(mse):
     return torch.log(mse) * (-10.0 / math.log(10.0))
 
 
+def _poll_networks(kw: dict) -> None:
+    """Raises if a fused kernel of either network reported a pipeline-barrier time-out so far (no synchronisation: one
+    read of pinned host memory per network).  A step whose kernels are still in flight is covered by the next call."""
+    for key in ("network_fn", "network_fine"):
+        n = kw.get(key)
+        if isinstance(n, nerf.NeRF) and n._fused is not None and not torch.cuda.is_current_stream_capturing():
+            n._fused.poll()
+
+
 def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwargs_train: dict, optimizer,
                lrate: float, lrate_decay: int, global_step: int, near: Optional[float] = None,
                far: Optional[float] = None) -> dict:
@@ -104,6 +113,7 @@ def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwarg
                 fin()
     optimizer.step()
     set_lrate(optimizer, decayed_lrate(lrate, lrate_decay, global_step))
+    _poll_networks(kw)
     out["loss"] = loss.detach()
     return out
 
@@ -163,7 +173,8 @@ class GraphedTrainStep:
             g.replay()                      # capture does not execute: this replay IS the step
         # the graph's Adam kernel moved the parameters behind torch's back: force the next non-graph user to re-pack
         for n in self._nets():
-            n._fused_version = None
+            n.invalidate_fused()
+        _poll_networks(self.kw)
         set_lrate(self.optimizer, decayed_lrate(self.lrate, self.lrate_decay, global_step))
         return self.out
 
