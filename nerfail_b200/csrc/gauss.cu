@@ -206,6 +206,53 @@ gauss_scatter_bwd_kernel(const float4* __restrict__ g_x, const float4* __restric
   }
 }
 
+// The same backward for NC cotangents of x_rgba at once (DeepFool's per-class gradients, deepfool.py:72-86: 14
+// torch.autograd.grad calls per iteration through the same forward): weights, indices, original pixel and the saved x are
+// read ONCE per pixel, the clip / alpha masks are evaluated once, and the NC gradient tables [NC][T][4] receive their
+// reductions from one launch.  g_xrgba [NC][B*HW][4]; g_x (the gradient w.r.t. the un-composited x) is not an input: the
+// classifier sees x_rgba only.
+__global__ void __launch_bounds__(256)
+gauss_scatter_bwd_batched_kernel(const float4* __restrict__ g_xrgba, int NC, const float4* __restrict__ x_saved,
+                                 const float* __restrict__ w_idx, const uint8_t* __restrict__ ori, int64_t B, int64_t HW,
+                                 float eps, int64_t T, float4* __restrict__ g_table) {
+  const int64_t n = B * HW;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, q = p % HW;
+    PixelIn px = load_pixel(w_idx, ori, b, q, HW);
+    const float4 x = ld_stream4(x_saved + p);
+    const float alpha = __fdiv_rn(x.w, 255.f);
+    const float xs[3] = {x.x, x.y, x.z};
+    bool pass[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float pr = __fmul_rn(xs[ch], alpha);
+      float v = pr;
+      bool ok = true;
+      if (eps >= 0.f) { ok = (pr >= -eps) && (pr <= eps); v = fminf(fmaxf(pr, -eps), eps); }
+      v = __fadd_rn(px.ori[ch], v);
+      pass[ch] = ok && (px.ori[3] > 0.f) && (v >= 0.f) && (v <= 255.f);
+    }
+    if (!(pass[0] || pass[1] || pass[2])) continue;           // this pixel passes no gradient for any cotangent
+#pragma unroll
+    for (int k = 0; k < 8; ++k) px.idx[k] = px.idx[k] < 0 ? 0 : (px.idx[k] >= T ? (int)(T - 1) : px.idx[k]);
+    for (int c = 0; c < NC; ++c) {
+      const float4 go = ld_stream4(g_xrgba + (int64_t)c * n + p);
+      const float gs[3] = {go.x, go.y, go.z};
+      float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+      float* Gp = &G.x;
+      float g_alpha = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch)
+        if (pass[ch]) { Gp[ch] = gs[ch] * alpha; g_alpha += gs[ch] * xs[ch]; }
+      G.w = g_alpha / 255.f;
+      float4* dst = g_table + (int64_t)c * T;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        red_add_v4(dst + px.idx[k], make_float4(G.x * px.w[k], G.y * px.w[k], G.z * px.w[k], G.w * px.w[k]));
+    }
+  }
+}
+
 static int stream_grid(int64_t items) {
   int64_t blocks = (items + 255) / 256;
   int64_t cap = (int64_t)sm_count() * 8;
@@ -332,6 +379,19 @@ int nfb_gauss_scatter_bwd(const float* g_x, const float* g_xrgba, const float* x
         reinterpret_cast<const float4*>(g_x), reinterpret_cast<const float4*>(g_xrgba),
         reinterpret_cast<const float4*>(x), w_idx, ori, B, HW, eps, T, reinterpret_cast<float4*>(g_table));
   return nfb::check_launch("gauss_scatter_bwd");
+}
+
+int nfb_gauss_scatter_bwd_batched(const float* g_xrgba, int NC, const float* x, const float* w_idx, const uint8_t* ori,
+                                  int64_t B, int64_t HW, float eps, int64_t T, float* g_table, void* stream) {
+  NFB_REQUIRE(g_xrgba && x && w_idx && ori && g_table, "gauss_scatter_bwd_batched: null pointer");
+  NFB_REQUIRE(NC >= 0 && T > 0 && B >= 0 && HW >= 0, "gauss_scatter_bwd_batched: bad size");
+  NFB_REQUIRE(((reinterpret_cast<uintptr_t>(g_table) | reinterpret_cast<uintptr_t>(w_idx) | reinterpret_cast<uintptr_t>(g_xrgba) |
+                reinterpret_cast<uintptr_t>(x)) & 15) == 0, "gauss_scatter_bwd_batched: buffers must be 16-byte aligned");
+  if (B * HW == 0 || NC == 0) return NFB_OK;
+  nfb::gauss_scatter_bwd_batched_kernel<<<nfb::stream_grid(B * HW), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(g_xrgba), NC, reinterpret_cast<const float4*>(x), w_idx, ori, B, HW, eps, T,
+      reinterpret_cast<float4*>(g_table));
+  return nfb::check_launch("gauss_scatter_bwd_batched");
 }
 
 int nfb_rgba_to_chw(const float* img_f32, const uint8_t* img_u8, const float* alpha_src, int64_t B, int64_t HW, float fill,

@@ -253,3 +253,47 @@ def sample_ray_batch(images, poses, i_train, H: int, W: int, K, N_rand: int, ste
     rays_d = rays_d[select_coords[:, 0], select_coords[:, 1]]
     target_s = target[select_coords[:, 0], select_coords[:, 1]][..., :3]
     return torch.stack([rays_o, rays_d], 0), target_s, img_i, select_coords
+
+
+# ---------------------------------------------------------------------------------------------
+# R:776-800  the core optimisation loop (loss, backward, Adam, exponential learning-rate decay)
+# ---------------------------------------------------------------------------------------------
+class Trainer:
+    """The reference's optimisation step on the CPU, functional weights: render the batch (R:776-778), loss =
+    img2mse(fine) + img2mse(coarse) (R:781-789, H:9), backward, torch.optim.Adam(lr, betas=(0.9, 0.999)) exactly as
+    create_nerf builds it (R:213), then lr = lrate * 0.1 ** (global_step / (lrate_decay * 1000)) (R:796-800).
+    Pinned by tests/golden/train_traj.npz (three steps of the unmodified reference, make_golden_train.py)."""
+
+    def __init__(self, sd_coarse, sd_fine, lrate: float = 5e-4, lrate_decay: int = 250):
+        self.sd_c = {k: v.clone().float().requires_grad_(True) for k, v in sd_coarse.items()}
+        self.sd_f = {k: v.clone().float().requires_grad_(True) for k, v in sd_fine.items()}
+        self.lrate, self.lrate_decay = lrate, lrate_decay
+        self.opt = torch.optim.Adam(list(self.sd_c.values()) + list(self.sd_f.values()), lr=lrate, betas=(0.9, 0.999))
+
+    def loss_and_outputs(self, rays: Tensor, target: Tensor, t_rand: Optional[Tensor] = None, u: Optional[Tensor] = None,
+                         n_samples: int = 64, n_importance: int = 128, white_bkgd: bool = True):
+        out = render_ray_batch(rays, self.sd_c, self.sd_f, n_samples, n_importance, white_bkgd, False, t_rand, u)
+        loss = torch.mean((out["rgb_map"] - target) ** 2) + torch.mean((out["rgb0"] - target) ** 2)
+        return loss, out
+
+    def step(self, rays: Tensor, target: Tensor, global_step: int, t_rand: Optional[Tensor] = None, u: Optional[Tensor] = None,
+             **kw) -> float:
+        self.opt.zero_grad()
+        loss, _ = self.loss_and_outputs(rays, target, t_rand, u, **kw)
+        loss.backward()
+        self.opt.step()
+        new_lrate = self.lrate * (0.1 ** (global_step / (self.lrate_decay * 1000)))
+        for gp in self.opt.param_groups:
+            gp["lr"] = new_lrate
+        return float(loss)
+
+    def state_dicts(self):
+        return ({k: v.detach().clone() for k, v in self.sd_c.items()}, {k: v.detach().clone() for k, v in self.sd_f.items()})
+
+
+def rays_from_batch(batch_rays: Tensor, near: float, far: float) -> Tensor:
+    """render(rays=batch_rays) of R:95-123 for use_viewdirs=True, ndc=False: [2,N,3] -> the [N,11] ray batch."""
+    o, d = batch_rays[0].float(), batch_rays[1].float()
+    v = d / torch.norm(d, dim=-1, keepdim=True)
+    n = torch.ones_like(d[:, :1])
+    return torch.cat([o, d, near * n, far * n, v], -1)

@@ -113,6 +113,72 @@ def test_training_step_gradients():
             np.testing.assert_allclose(np.linalg.norm(p.grad.numpy().astype(np.float64)), g[f"norm.{key}"], rtol=1e-4, atol=1e-9)
 
 
+def test_training_trajectory_with_adam_and_lr_decay():
+    """oracle Trainer (R:776-800) against three optimisation steps of the unmodified reference (make_golden_train.py):
+    the losses agree to 1e-5 and every weight tensor ends where the reference's did (Adam is torch's in both)."""
+    g = golden("train_traj.npz")
+    tr = no.Trainer(synth.make_non_degenerate(synth.random_state_dict(0), 0), synth.make_non_degenerate(synth.random_state_dict(1), 1))
+    for i, gs in enumerate(g["global_steps"]):
+        rays = no.rays_from_batch(T(g["batch_rays"][i]), 2.0, 6.0)
+        np.random.seed(0); t_rand = torch.Tensor(np.random.rand(rays.shape[0], 64))      # the reference's pytest hook
+        np.random.seed(0); u = torch.Tensor(np.random.rand(rays.shape[0], 128))
+        loss = tr.step(rays, T(g["targets"][i]), int(gs), t_rand, u)
+        assert abs(loss - g["losses"][i]) <= 1e-5 * abs(g["losses"][i]) + 1e-7, (i, loss, g["losses"][i])
+    assert abs(tr.opt.param_groups[0]["lr"] - 5e-4 * 0.1 ** (2 / 250000)) < 1e-12
+    init = {"c": synth.make_non_degenerate(synth.random_state_dict(0), 0), "f": synth.make_non_degenerate(synth.random_state_dict(1), 1)}
+    for tag, sd in (("c", tr.sd_c), ("f", tr.sd_f)):
+        for name, p in sd.items():
+            key = f"{tag}.{name}"
+            moved = float((p.detach() - init[tag][name]).norm())
+            assert moved > 0, key
+            if key in g:        # the update itself (3 Adam steps of ~lr each) matches to 1 % of its own size
+                assert float((p.detach() - T(g[key])).norm()) < 1e-2 * moved, (key, moved)
+            np.testing.assert_allclose(np.linalg.norm(p.detach().numpy().astype(np.float64)), g[f"norm.{key}"], rtol=1e-6)
+
+
+def test_knife_edge_of_deterministic_sampling():
+    """Why the fine pass of a deterministic render (perturb = 0) cannot be held to 1e-3 on EVERY pixel by any second
+    implementation: the experiment on the reference's own arithmetic (the oracle is bit-exact against it, see above).
+    Perturb the reference's coarse weights by ONE ulp (random direction) and redo resampling + fine pass:
+      * with u = linspace(0, 1, 128) the last sample sits at u == 1.0 == cdf[-1] up to rounding and empty bins sit at the
+        `denom < 1e-5` switch of run_nerf_helpers.py:237-238, so z_std changes on > 10 % of the rays — several times (measured 10x at 40x40) the rate
+        of the stochastic path (random u) under the same perturbation;
+      * the rendered colour then moves by > 1e-4 of its scale on some rays: a 6e-8 relative input change amplified > 1000x,
+        i.e. to the order of the 1e-3 parity bar itself, while staying under the 3e-3 the GPU tests allow for such rays.
+    tests/test_gpu_render.py / test_gpu_fullsize.py therefore gate the fine pass at ">= 95 % of the pixels within 1e-3,
+    every pixel within 3e-3" and the coarse pass (no sampling decision upstream) at 1e-3 everywhere."""
+    H = W = 24
+    K, _ = synth.intrinsics(H, W)
+    rays = no.camera_rays(H, W, K, torch.tensor(synth.pose_spherical(30.0, -30.0, 4.0)[:3, :4]), 2.0, 6.0)
+    sd_c = synth.make_non_degenerate(synth.random_state_dict(0), 0)
+    sd_f = synth.make_non_degenerate(synth.random_state_dict(1), 1)
+    o, d, v = rays[:, 0:3], rays[:, 3:6], rays[:, 8:11]
+    gen = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        z = no.coarse_depths(rays, 64)
+        raw = no.query_network(sd_c, o[:, None] + d[:, None] * z[..., None], v)
+        _, _, _, w0, _ = no.composite(raw, z, d, True)
+
+        def fine(zf):
+            return no.composite(no.query_network(sd_f, o[:, None] + d[:, None] * zf[..., None], v), zf, d, True)[0]
+
+        rate, worst = {}, {}
+        for name, u in (("det", None), ("rand", torch.rand(rays.shape[0], 128, generator=gen))):
+            zf, _, zstd = no.hierarchical_depths(z, w0, 128, u)
+            rgb = fine(zf)
+            changed, moved = [], []
+            for _ in range(3):
+                up = torch.rand(w0.shape, generator=gen) < 0.5
+                w1 = torch.where(up, torch.nextafter(w0, torch.full_like(w0, 2.0)), torch.nextafter(w0, torch.full_like(w0, -1.0)))
+                zf1, _, zstd1 = no.hierarchical_depths(z, w1, 128, u)
+                changed.append(float(((zstd1 - zstd).abs() > 1e-6).float().mean()))
+                moved.append(float((fine(zf1) - rgb).abs().max() / rgb.abs().max()))
+            rate[name], worst[name] = float(np.mean(changed)), float(np.max(moved))
+    assert rate["det"] > 0.10, rate
+    assert rate["det"] > 4 * rate["rand"], rate
+    assert 1e-4 < worst["det"] < 3e-3, worst
+
+
 def test_gaussnet():
     g = golden("gauss.npz")
     s, di, ori = T(g["spatial_rgb"]), T(g["dist_idx"]), T(g["ori"])
