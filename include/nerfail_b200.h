@@ -33,7 +33,7 @@ extern "C" {
 #define NFB_E_UNSUPPORTED -2   /* shape outside what the sm_100a kernels are built for          */
 #define NFB_E_CUDA        -3   /* CUDA runtime error (text in nfb_last_error)                    */
 
-#define NFB_ABI_VERSION    1
+#define NFB_ABI_VERSION    2
 
 #if defined(__GNUC__)
 #define NFB_API __attribute__((visibility("default")))
@@ -63,6 +63,14 @@ NFB_API int nfb_get_rays(int H, int W, const double* K_host, const float* c2w_ho
  * rays [R,11]; t_rand [R,S] uniform numbers or NULL (perturb == 0); z_vals out [R,S].               */
 NFB_API int nfb_coarse_z(const float* rays, int R, int S, int lindisp, const float* t_rand,
                  float* z_vals, void* stream);
+/* The same with the stratified jitter drawn IN the kernel (replaces the torch.rand of run_nerf.py:371 and its [R,S] HBM
+ * tensor): element p = r*S + i is word p & 3 of Philox4x32-10 at counter (p >> 2, stream 0, offset) under key `seed`,
+ * mapped to [0,1) with 24 bits like torch.rand.  Same seed + offset -> same depths; advance offset per call.          */
+/* The generator by itself: out[p] for p < n of stream `stream_id` (0 = coarse jitter, 1 = inverse-CDF u); lets a caller or a
+ * test reproduce exactly the numbers nfb_coarse_z_rng / nfb_hierarchical_rng consume.                                 */
+NFB_API int nfb_philox_uniform(uint64_t seed, uint64_t offset, uint32_t stream_id, int64_t n, float* out, void* stream);
+NFB_API int nfb_coarse_z_rng(const float* rays, int R, int S, int lindisp, uint64_t seed, uint64_t offset,
+                             float* z_vals, void* stream);
 
 /* Opaque network handle: bf16 weight images pre-swizzled for tcgen05 + fp32 biases and heads. */
 typedef struct nfb_mlp nfb_mlp_t;
@@ -210,18 +218,23 @@ NFB_API int nfb_sample_pdf(const float* bins, const float* weights, int w_pitch,
  * z_std [R] (or NULL).  Requires 3 <= Sc <= 128, Sc+N <= 512.                                         */
 NFB_API int nfb_hierarchical(const float* z_coarse, const float* weights, const float* u, int R, int Sc, int N,
                      float* z_fine, float* z_samples, float* z_std, void* stream);
+/* The same with u drawn in the kernel (replaces the torch.rand of run_nerf_helpers.py:213): Philox stream 1 of the
+ * generator described at nfb_coarse_z_rng, element r*N + k.                                                           */
+NFB_API int nfb_hierarchical_rng(const float* z_coarse, const float* weights, uint64_t seed, uint64_t offset, int R, int Sc,
+                                 int N, float* z_fine, float* z_samples, float* z_std, void* stream);
 
 /* One ray batch, coarse + fine, without autograd: the whole kernel sequence of render_rays in one call.
  * replaces: run_nerf.py:308-418 (render_rays; nerf_to_coord.py:320-433 when pts_max != NULL) under torch.no_grad() with
  * raw_noise_std = 0: coarse depths -> fused MLP -> compositing -> inverse-CDF resampling + merge -> fused MLP -> compositing.
- * rays [R,11]; t_rand [R,N_samples] / u [R,N_importance] uniform numbers or NULL (perturb == 0);
+ * rays [R,11]; t_rand [R,N_samples] / u [R,N_importance]: the caller's uniform numbers, or NULL: deterministic sampling when
+ * perturb == 0, else numbers drawn in the kernels (nfb_coarse_z_rng / nfb_hierarchical_rng with rng_seed, rng_offset);
  * outputs rgb [R,3], disp [R], acc [R] (+ rgb0 / disp0 / acc0 / z_std [R] when N_importance > 0, else ignored),
  * pts_max [R,3] or NULL.  fine may be NULL (the coarse network is queried twice, run_nerf.py:399).
  * workspace: nfb_render_rays_workspace_bytes(R, N_samples, N_importance) bytes, 256-byte aligned, caller-owned.     */
 NFB_API size_t nfb_render_rays_workspace_bytes(int R, int N_samples, int N_importance);
 NFB_API int nfb_render_rays_fwd(const nfb_mlp_t* coarse, const nfb_mlp_t* fine, const float* rays, int R, int N_samples,
                                 int N_importance, int lindisp, int white_bkgd, const float* t_rand, const float* u,
-                                float* rgb, float* disp, float* acc, float* rgb0, float* disp0, float* acc0, float* z_std,
+                                int perturb, uint64_t rng_seed, uint64_t rng_offset, float* rgb, float* disp, float* acc, float* rgb0, float* disp0, float* acc0, float* z_std,
                                 float* pts_max, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- */
@@ -269,6 +282,12 @@ NFB_API int nfb_gauss_scatter_bwd(const float* g_x, const float* g_xrgba, const 
                           const uint8_t* ori, int64_t B, int64_t HW, float eps, int64_t T,
                           float* g_table, void* stream);
 
+/* The same backward for NC cotangents of x_rgba in ONE launch — the per-class gradients of DeepFool (deepfool.py:72-86: 14
+ * torch.autograd.grad calls per iteration through the same forward).  g_xrgba [NC,B,HW,4]; weights, indices, the original
+ * pixel and the saved x are read once per pixel; g_table [NC,T,4] is ACCUMULATED into (caller zeroes it).                */
+NFB_API int nfb_gauss_scatter_bwd_batched(const float* g_xrgba, int NC, const float* x, const float* w_idx, const uint8_t* ori,
+                                          int64_t B, int64_t HW, float eps, int64_t T, float* g_table, void* stream);
+
 /* replaces: model/GaussNet.py:121-145 — NHWC RGBA -> NCHW RGB, white where alpha is 0 (the classifier's input).
  * img_f32 [B,HW,4] float or img_u8 [B,HW,4] uint8 (exactly one non-NULL); alpha_src [B,HW,4] float whose channel 3
  * decides (NULL: the image's own channel 3); out [B,3,HW] = alpha > 0 ? rgb : fill (255 in the reference).
@@ -278,6 +297,33 @@ NFB_API int nfb_rgba_to_chw(const float* img_f32, const uint8_t* img_u8, const f
                             float fill, float* out, void* stream);
 NFB_API int nfb_chw_to_rgba(const float* g_out, const float* alpha_src, int64_t B, int64_t HW, float* g_img, void* stream);
 
+/* nfb_rgba_to_chw with the classifier's bilinear Resize fused behind it.
+ * replaces: model/GaussNet.py:121-145 + :147-154 (torchvision.transforms.Resize([299,299]) / ([224,224]) on the float NCHW
+ * tensor = ATen upsample_bilinear2d, align_corners = False; antialias selects _upsample_bilinear2d_aa, the default of
+ * current torchvision for tensors, off in the torchvision 0.15 the reference pins).
+ * A resize is separable: per axis and OUTPUT index a first tap, a tap count and normalised weights.  nfb_resize_weights
+ * fills them on the HOST (fp32, ATen's formulas) for one axis: start / count [n], weights [n][maxk] with n = out_size, or,
+ * transposed != 0, per INPUT index (n = in_size) the contiguous range of outputs it feeds — the table of the adjoint.
+ * maxk >= nfb_resize_max_taps(...).  The caller uploads the tables once per (in, out, antialias).
+ * nfb_rgba_to_chw_resized: out [B,3,OH,OW] = resize(alpha > 0 ? rgb : fill); alpha from channel 3 of the image itself or,
+ * alpha_src != NULL, of alpha_src [alpha_batch,H*W,4] (image b uses b % alpha_batch).
+ * nfb_chw_resized_to_rgba: its adjoint, g_img [B,H*W,4] = alpha > 0 ? (resize^T g_out, 0) : 0 — a gather through the
+ * transposed tables, deterministic.  The pair is linear, each the other's derivative: differentiable twice (deepfool.py:76-77).
+ * With B = NC * alpha_batch the adjoint serves NC cotangents of the same alpha_batch images in one launch.                 */
+NFB_API int nfb_resize_max_taps(int in_size, int out_size, int antialias, int transposed);
+NFB_API int nfb_resize_weights(int in_size, int out_size, int antialias, int transposed, int maxk,
+                               int* start_host, int* count_host, float* weights_host);
+NFB_API int nfb_rgba_to_chw_resized(const float* img_f32, const uint8_t* img_u8, const float* alpha_src, int64_t alpha_batch,
+                                    int64_t B, int H, int W, int OH, int OW, float fill,
+                                    const int* y_start, const int* y_count, const float* y_w, int y_maxk,
+                                    const int* x_start, const int* x_count, const float* x_w, int x_maxk,
+                                    float* out, void* stream);
+NFB_API int nfb_chw_resized_to_rgba(const float* g_out, const float* alpha_src, int64_t alpha_batch, int64_t B, int H, int W,
+                                    int OH, int OW,
+                                    const int* yt_start, const int* yt_count, const float* yt_w, int yt_maxk,
+                                    const int* xt_start, const int* xt_count, const float* xt_w, int xt_maxk,
+                                    float* g_img, void* stream);
+
 /* The I-FGSM update of attack_NeRFail_S.py:357-392 restricted to the rows it can change (alpha > 0; active_idx [n] int64 row
  * numbers of the [T,4] perturbation table, fixed for a whole attack).  nfb_attack_pack_rgb packs the RGB gradient of those
  * rows, [n,3], which is all a data-parallel attack has to all-reduce; nfb_attack_sign_step applies
@@ -285,6 +331,44 @@ NFB_API int nfb_chw_to_rgba(const float* g_out, const float* alpha_src, int64_t 
 NFB_API int nfb_attack_pack_rgb(const float* grad, const int64_t* active_idx, int64_t n, float* packed, void* stream);
 NFB_API int nfb_attack_sign_step(float* table, const float* init, const int64_t* active_idx, const float* packed_grad,
                                  int64_t n, float signed_step, float eps, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* C. Multi-GPU exchange steps over NVLink peer memory (one process per GPU)   */
+/* ------------------------------------------------------------------------- */
+
+/* Peer memory: a cudaMalloc allocation (zero-filled) that the other ranks of the node open through a 64-byte CUDA IPC handle
+ * (exchanged by the host side, e.g. torch.distributed.all_gather_object); peer access is enabled on first open.
+ * nfb_peer_create binds, for a group of G <= 8 ranks, every rank's gradient buffer, every rank's copy of the quantity
+ * being updated and every rank's flag words (nfb_peer_flag_bytes() bytes, zero-filled) — arrays of G pointers indexed by
+ * rank, own buffers included.  All ranks must call the exchange steps in the same order (collective semantics).
+ * nfb_peer_status: NFB_E_CUDA once a flag wait timed out (a rank never arrived); sticky, no synchronisation.          */
+typedef struct nfb_peer nfb_peer_t;
+NFB_API int nfb_peer_alloc(size_t bytes, void** out);
+NFB_API int nfb_peer_free(void* p);
+NFB_API int nfb_peer_export(void* p, void* handle64);
+NFB_API int nfb_peer_import(const void* handle64, void** out);
+NFB_API int nfb_peer_close(void* p);
+NFB_API int nfb_peer_flag_bytes(void);
+NFB_API int nfb_peer_create(nfb_peer_t** out, int rank, int G, void* const* grad_ptrs, void* const* value_ptrs,
+                            void* const* flag_ptrs);
+NFB_API int nfb_peer_destroy(nfb_peer_t* h);
+NFB_API int nfb_peer_status(const nfb_peer_t* h);
+
+/* One attack iteration's exchange as ONE kernel per GPU.
+ * replaces: the gradient reduction a data-parallel run of attack_NeRFail_S.py:348 needs + the I-FGSM update of :357-392.
+ * grad buffers [T,4] hold each rank's partial grad_spatial_rgb (its views' scatter), value buffers [T,4] each rank's copy
+ * of the perturbation table.  Rank r owns rows [r*ceil(T/G), ...): for its rows with A > 0 it sums the G partial
+ * gradients through peer loads, applies rgb <- clamp(rgb - signed_step * sign(g), init - eps, init + eps) and stores the
+ * row into every rank's table.  On return (stream order) this rank's table is final and its gradient buffer may be zeroed. */
+NFB_API int nfb_attack_exchange_step(nfb_peer_t* h, const float* init, int64_t T, float signed_step, float eps, void* stream);
+
+/* One retraining step's exchange + optimiser as ONE kernel per GPU.
+ * replaces: the gradient average a data-parallel run of run_nerf.py:791 needs + optimizer.step() of :792 (torch.optim.Adam,
+ * arithmetic of nfb_adam_step).  grad / value buffers are the flat [n] gradients / parameters (padded to a multiple of 4
+ * floats) of ALL parameters in optimiser order; exp_avg / exp_avg_sq [n] are local (only this rank's slice is used: the
+ * optimiser state is sharded).  step_scalars: device [2] as nfb_adam_step_dev.  grad_scale = 1 / G for a mean.           */
+NFB_API int nfb_adam_exchange_step(nfb_peer_t* h, float* exp_avg, float* exp_avg_sq, int64_t n, const float* step_scalars,
+                                   double beta1, double beta2, double eps, double grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

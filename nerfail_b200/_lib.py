@@ -26,6 +26,8 @@ SIGNATURES = {
     "nfb_device_cc": (c_int, []),
     "nfb_get_rays": (c_int, [c_int, c_int, c_ptr, c_ptr, C.c_float, C.c_float, c_ptr, c_ptr]),
     "nfb_coarse_z": (c_int, [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "nfb_philox_uniform": (c_int, [C.c_uint64, C.c_uint64, C.c_uint32, c_i64, c_ptr, c_ptr]),
+    "nfb_coarse_z_rng": (c_int, [c_ptr, c_int, c_int, c_int, C.c_uint64, C.c_uint64, c_ptr, c_ptr]),
     "nfb_mlp_create": (c_int, [C.POINTER(c_ptr), c_int, c_int, c_int, c_int, c_int]),
     "nfb_mlp_update": (c_int, [c_ptr, c_ptr, c_i64, c_ptr]),
     "nfb_mlp_destroy": (c_int, [c_ptr]),
@@ -47,8 +49,8 @@ SIGNATURES = {
     "nfb_mlp_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_wgrad_bf16": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_i64, c_int, c_i64, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "nfb_render_rays_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
-    "nfb_render_rays_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr] + [c_ptr] * 8
-                            + [c_ptr, C.c_size_t, c_ptr]),
+    "nfb_render_rays_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
+                                    c_int, C.c_uint64, C.c_uint64] + [c_ptr] * 8 + [c_ptr, C.c_size_t, c_ptr]),
     "nfb_attack_pack_rgb": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "nfb_attack_sign_step": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, C.c_float, C.c_float, c_ptr]),
     "nfb_rgba_to_chw": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr]),
@@ -60,12 +62,31 @@ SIGNATURES = {
     "nfb_composite_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_sample_pdf": (c_int, [c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "nfb_hierarchical": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_hierarchical_rng": (c_int, [c_ptr, c_ptr, C.c_uint64, C.c_uint64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_knn8": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_knn_grid_cells": (c_i64, []),
     "nfb_knn_grid_build": (c_int, [c_ptr, c_i64, c_ptr, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_knn8_grid": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, C.c_float, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_peer_alloc": (c_int, [C.c_size_t, C.POINTER(c_ptr)]),
+    "nfb_peer_free": (c_int, [c_ptr]),
+    "nfb_peer_export": (c_int, [c_ptr, c_ptr]),
+    "nfb_peer_import": (c_int, [c_ptr, C.POINTER(c_ptr)]),
+    "nfb_peer_close": (c_int, [c_ptr]),
+    "nfb_peer_flag_bytes": (c_int, []),
+    "nfb_peer_create": (c_int, [C.POINTER(c_ptr), c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "nfb_peer_destroy": (c_int, [c_ptr]),
+    "nfb_peer_status": (c_int, [c_ptr]),
+    "nfb_attack_exchange_step": (c_int, [c_ptr, c_ptr, c_i64, C.c_float, C.c_float, c_ptr]),
+    "nfb_adam_exchange_step": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, C.c_double, C.c_double, C.c_double, C.c_double, c_ptr]),
     "nfb_gauss_weights": (c_int, [c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr]),
     "nfb_gauss_gather_fwd": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nfb_gauss_scatter_bwd_batched": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_i64, c_ptr, c_ptr]),
+    "nfb_resize_max_taps": (c_int, [c_int, c_int, c_int, c_int]),
+    "nfb_resize_weights": (c_int, [c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "nfb_rgba_to_chw_resized": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int, C.c_float,
+                                        c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr]),
+    "nfb_chw_resized_to_rgba": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_int, c_int,
+                                        c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr]),
     "nfb_gauss_scatter_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_i64, c_ptr, c_ptr]),
 }
 
@@ -88,7 +109,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.nfb_abi_version() != 1:
+    if lib.nfb_abi_version() != 2:
         raise RuntimeError("libnerfail_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

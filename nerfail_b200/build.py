@@ -19,7 +19,7 @@ OUT_DIR = PKG / "_lib"
 LIB = OUT_DIR / "libnerfail_b200.so"
 STAMP = OUT_DIR / "build.stamp"
 
-SOURCES = ["api.cu", "composite.cu", "sampling.cu", "gauss.cu", "knn.cu", "linear.cu", "mlp_fused.cu", "wgrad.cu", "optim.cu"]
+SOURCES = ["api.cu", "composite.cu", "sampling.cu", "gauss.cu", "resize.cu", "peer.cu", "knn.cu", "linear.cu", "mlp_fused.cu", "wgrad.cu", "optim.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -60,7 +60,7 @@ size_t nfb_render_rays_workspace_bytes(int R, int N_samples, int N_importance) {
 
 int nfb_render_rays_fwd(const nfb_mlp_t* coarse, const nfb_mlp_t* fine, const float* rays, int R, int N_samples,
                         int N_importance, int lindisp, int white_bkgd, const float* t_rand, const float* u,
-                        float* rgb, float* disp, float* acc, float* rgb0, float* disp0, float* acc0, float* z_std,
+                        int perturb, uint64_t rng_seed, uint64_t rng_offset, float* rgb, float* disp, float* acc, float* rgb0, float* disp0, float* acc0, float* z_std,
                         float* pts_max, void* workspace, size_t workspace_bytes, void* stream) {
   NFB_REQUIRE(coarse && rays && rgb && disp && acc, "render_rays_fwd: null pointer");
   NFB_REQUIRE(N_importance == 0 || (rgb0 && disp0 && acc0), "render_rays_fwd: coarse outputs are required when N_importance > 0");
@@ -74,14 +74,18 @@ int nfb_render_rays_fwd(const nfb_mlp_t* coarse, const nfb_mlp_t* fine, const fl
   float* raw = reinterpret_cast<float*>(w);  w += align256(r * Sf * 16);
   float* wts = reinterpret_cast<float*>(w);  w += align256(r * Sf * 4);
   float* z_f = reinterpret_cast<float*>(w);
-  int rc = nfb_coarse_z(rays, R, N_samples, lindisp, t_rand, z_c, stream);                            // run_nerf.py:357-379
+  // stratified draws: the caller's numbers when given, else (perturb != 0) Philox in the kernels, else deterministic
+  const bool rng_t = perturb && !t_rand, rng_u = perturb && !u;
+  int rc = rng_t ? nfb_coarse_z_rng(rays, R, N_samples, lindisp, rng_seed, rng_offset, z_c, stream)
+                 : nfb_coarse_z(rays, R, N_samples, lindisp, t_rand, z_c, stream);                     // run_nerf.py:357-379
   if (rc == NFB_OK) rc = nfb_mlp_fwd(coarse, 1, nullptr, nullptr, rays, z_c, R, N_samples, raw, stream);   // :381-385
   const bool two = N_importance > 0;
   if (rc == NFB_OK)                                                                                     // :386
     rc = nfb_composite_fwd(raw, z_c, rays + 3, 11, nullptr, R, N_samples, white_bkgd, two ? rgb0 : rgb, two ? disp0 : disp,
                            two ? acc0 : acc, wts, nullptr, two ? nullptr : pts_max, stream);
   if (rc != NFB_OK || !two) return rc;
-  rc = nfb_hierarchical(z_c, wts, u, R, N_samples, N_importance, z_f, nullptr, z_std, stream);         // :392-396, :412
+  rc = rng_u ? nfb_hierarchical_rng(z_c, wts, rng_seed, rng_offset, R, N_samples, N_importance, z_f, nullptr, z_std, stream)
+             : nfb_hierarchical(z_c, wts, u, R, N_samples, N_importance, z_f, nullptr, z_std, stream);  // :392-396, :412
   if (rc == NFB_OK) rc = nfb_mlp_fwd(fine ? fine : coarse, 1, nullptr, nullptr, rays, z_f, R, (int)Sf, raw, stream);   // :397-401
   if (rc == NFB_OK)                                                                                     // :403, nerf_to_coord.py:418-421
     rc = nfb_composite_fwd(raw, z_f, rays + 3, 11, nullptr, R, (int)Sf, white_bkgd, rgb, disp, acc, wts, nullptr, pts_max, stream);

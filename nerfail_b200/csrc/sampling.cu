@@ -20,6 +20,31 @@ __device__ __forceinline__ float linspace01(int i, int n) {
   return (i < n / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(n - 1 - i), 1.f);
 }
 
+// In-kernel uniform numbers for the stochastic render path (run_nerf.py:365-379 t_rand, run_nerf_helpers.py:213 u): the
+// reference draws them with torch.rand into [R,64] + [R,128] HBM tensors; here element p of stream `sid` is word p & 3 of
+// Philox4x32-10 (Salmon et al. 2011 — the counter-based generator torch.cuda itself uses) at counter (p >> 2, sid, offset)
+// under key `seed`, mapped to [0, 1) with 24 bits like torch.rand.  Stateless: any thread can produce any element.
+struct Rng { unsigned long long seed, offset; int on; };
+__device__ __forceinline__ float philox_uniform(const Rng& g, uint32_t sid, uint64_t p) {
+  uint32_t c0 = (uint32_t)(p >> 2), c1 = (uint32_t)(p >> 34), c2 = sid ^ (uint32_t)(g.offset >> 32), c3 = (uint32_t)g.offset;
+  uint32_t k0 = (uint32_t)g.seed, k1 = (uint32_t)(g.seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const uint32_t w = (p & 3) == 0 ? c0 : (p & 3) == 1 ? c1 : (p & 3) == 2 ? c2 : c3;
+  return (float)(w >> 8) * 5.9604644775390625e-08f;      // 2^-24
+}
+
+__global__ void philox_uniform_kernel(Rng rng, uint32_t sid, int64_t n, float* __restrict__ out) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    out[p] = philox_uniform(rng, sid, (uint64_t)p);
+}
+
 __global__ void get_rays_kernel(int H, int W, float fx, float fy, float cx, float cy,
                                 float r00, float r01, float r02, float r10, float r11, float r12,
                                 float r20, float r21, float r22, float tx, float ty, float tz,
@@ -51,18 +76,19 @@ __device__ __forceinline__ float coarse_depth(float near_, float far_, int i, in
 }
 
 __global__ void coarse_z_kernel(const float* __restrict__ rays, int R, int S, int lindisp,
-                                const float* __restrict__ t_rand, float* __restrict__ z_vals) {
+                                const float* __restrict__ t_rand, const Rng rng, float* __restrict__ z_vals) {
   const int64_t n = (int64_t)R * S;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(p / S), i = (int)(p % S);
     const float near_ = __ldg(rays + (int64_t)r * 11 + 6), far_ = __ldg(rays + (int64_t)r * 11 + 7);
     float zc = coarse_depth(near_, far_, i, S, lindisp);
-    if (t_rand) {   // run_nerf.py:365-379
+    if (t_rand || rng.on) {   // run_nerf.py:365-379
       const float zl = (i > 0) ? coarse_depth(near_, far_, i - 1, S, lindisp) : zc;
       const float zu = (i + 1 < S) ? coarse_depth(near_, far_, i + 1, S, lindisp) : zc;
       const float lower = (i > 0) ? __fmul_rn(0.5f, __fadd_rn(zc, zl)) : zc;
       const float upper = (i + 1 < S) ? __fmul_rn(0.5f, __fadd_rn(zu, zc)) : zc;
-      zc = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(t_rand + p)));
+      const float t = t_rand ? __ldg(t_rand + p) : philox_uniform(rng, 0u, (uint64_t)p);
+      zc = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t));
     }
     z_vals[p] = zc;
   }
@@ -197,7 +223,7 @@ sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weig
 // (coarse elements first among equals), ~40x fewer instructions than sorting all 192 values from scratch.
 __global__ void __launch_bounds__(128)
 hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict__ weights,
-                    const float* __restrict__ u, int R, int Sc, int N, int P,
+                    const float* __restrict__ u, const Rng rng, int R, int Sc, int N, int P,
                     float* __restrict__ z_fine, float* __restrict__ z_samples, float* __restrict__ z_std) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -218,7 +244,8 @@ hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict_
     build_cdf(weights + (int64_t)r * Sc + 1, nb - 1, cdf, lane);                                // weights[...,1:-1]
     float sum = 0.f;
     for (int k = lane; k < N; k += 32) {
-      const float uk = u ? __ldg(u + (int64_t)r * N + k) : linspace01(k, N);
+      const float uk = u ? __ldg(u + (int64_t)r * N + k)
+                         : (rng.on ? philox_uniform(rng, 1u, (uint64_t)r * N + k) : linspace01(k, N));
       const float s = invert_cdf(cdf_a, sb_a, nb, uk, nullptr);
       zs[k] = s;
       sum += s;
@@ -237,7 +264,7 @@ hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict_
     bool unsorted = false;
     for (int k = lane; k + 1 < N; k += 32) unsorted |= zs[k] > zs[k + 1];
     unsorted = __any_sync(FULL, unsorted);
-    if (unsorted && !u) {
+    if (unsorted && !u && !rng.on) {
       // deterministic u: inversions are isolated adjacent pairs at bin boundaries; a few odd-even transposition rounds
       // repair them for ~60 instructions each instead of the 28-pass bitonic network (which was 3/4 of this kernel)
       for (int round = 0; round < 4 && unsorted; ++round) {
@@ -313,12 +340,27 @@ int nfb_get_rays(int H, int W, const double* K, const float* c, float near_, flo
   return nfb::check_launch("get_rays");
 }
 
-int nfb_coarse_z(const float* rays, int R, int S, int lindisp, const float* t_rand, float* z_vals, void* stream) {
+static int coarse_z_launch(const float* rays, int R, int S, int lindisp, const float* t_rand, nfb::Rng rng, float* z_vals, void* stream) {
   NFB_REQUIRE(rays && z_vals && R >= 0 && S > 0, "coarse_z: R=%d S=%d", R, S);
   if (R == 0) return NFB_OK;
   nfb::coarse_z_kernel<<<nfb::grid_for((int64_t)R * S, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      rays, R, S, lindisp, t_rand, z_vals);
+      rays, R, S, lindisp, t_rand, rng, z_vals);
   return nfb::check_launch("coarse_z");
+}
+
+int nfb_coarse_z(const float* rays, int R, int S, int lindisp, const float* t_rand, float* z_vals, void* stream) {
+  return coarse_z_launch(rays, R, S, lindisp, t_rand, nfb::Rng{0ull, 0ull, 0}, z_vals, stream);
+}
+
+int nfb_philox_uniform(uint64_t seed, uint64_t offset, uint32_t stream_id, int64_t n, float* out, void* stream) {
+  NFB_REQUIRE(out && n >= 0, "philox_uniform: bad argument");
+  if (n == 0) return NFB_OK;
+  nfb::philox_uniform_kernel<<<nfb::grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(nfb::Rng{seed, offset, 1}, stream_id, n, out);
+  return nfb::check_launch("philox_uniform");
+}
+
+int nfb_coarse_z_rng(const float* rays, int R, int S, int lindisp, uint64_t seed, uint64_t offset, float* z_vals, void* stream) {
+  return coarse_z_launch(rays, R, S, lindisp, nullptr, nfb::Rng{seed, offset, 1}, z_vals, stream);
 }
 
 int nfb_sample_pdf(const float* bins, const float* weights, int w_pitch, const float* u,
@@ -337,8 +379,8 @@ int nfb_sample_pdf(const float* bins, const float* weights, int w_pitch, const f
   return nfb::check_launch("sample_pdf");
 }
 
-int nfb_hierarchical(const float* z_coarse, const float* weights, const float* u, int R, int Sc, int N,
-                     float* z_fine, float* z_samples, float* z_std, void* stream) {
+static int hierarchical_launch(const float* z_coarse, const float* weights, const float* u, nfb::Rng rng, int R, int Sc, int N,
+                               float* z_fine, float* z_samples, float* z_std, void* stream) {
   NFB_REQUIRE(z_coarse && weights && z_fine, "hierarchical: null pointer");
   NFB_REQUIRE(R >= 0 && N > 0, "hierarchical: R=%d N=%d", R, N);
   if (Sc < 3 || Sc > 128 || Sc + N > 512)
@@ -348,8 +390,18 @@ int nfb_hierarchical(const float* z_coarse, const float* weights, const float* u
   while (P < N) P <<= 1;
   const size_t smem = (size_t)4 * (2 * (Sc - 1) + Sc + P + Sc + N) * sizeof(float);
   nfb::hierarchical_kernel<<<nfb::grid_for(R, 4, 16), 128, smem, (cudaStream_t)stream>>>(
-      z_coarse, weights, u, R, Sc, N, P, z_fine, z_samples, z_std);
+      z_coarse, weights, u, rng, R, Sc, N, P, z_fine, z_samples, z_std);
   return nfb::check_launch("hierarchical");
+}
+
+int nfb_hierarchical(const float* z_coarse, const float* weights, const float* u, int R, int Sc, int N,
+                     float* z_fine, float* z_samples, float* z_std, void* stream) {
+  return hierarchical_launch(z_coarse, weights, u, nfb::Rng{0ull, 0ull, 0}, R, Sc, N, z_fine, z_samples, z_std, stream);
+}
+
+int nfb_hierarchical_rng(const float* z_coarse, const float* weights, uint64_t seed, uint64_t offset, int R, int Sc, int N,
+                         float* z_fine, float* z_samples, float* z_std, void* stream) {
+  return hierarchical_launch(z_coarse, weights, nullptr, nfb::Rng{seed, offset, 1}, R, Sc, N, z_fine, z_samples, z_std, stream);
 }
 
 }  // extern "C"

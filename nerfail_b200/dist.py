@@ -121,10 +121,18 @@ def allreduce_active_rgb(grad: torch.Tensor, active_idx: torch.Tensor) -> torch.
 
 
 def attack_sign_step_(spatial_rgb: torch.Tensor, grad: torch.Tensor, init: torch.Tensor, step: float, eps: float,
-                      minimise: bool = True, active_idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      minimise: bool = True, active_idx: Optional[torch.Tensor] = None,
+                      exchange: Optional["PeerExchange"] = None) -> torch.Tensor:
     """The I-FGSM update of attack_NeRFail_S.py:357-392 applied AFTER the gradient all-reduce: sign step on the RGB
     channels where the point is active (A > 0), then clamp to init +- eps.  Identical on every rank by construction.
-    With active_idx (= active_rows(spatial_rgb)) only those rows are exchanged and updated; the result is the same."""
+    With active_idx (= active_rows(spatial_rgb)) only those rows are exchanged and updated; the result is the same.
+    With exchange (a PeerExchange whose `value` IS spatial_rgb and whose `grad` IS grad) the reduction, the update and the
+    broadcast are one kernel per GPU over NVLink peer memory instead of an NCCL all-reduce plus an update kernel."""
+    if exchange is not None:
+        if spatial_rgb.data_ptr() != exchange.value.data_ptr() or grad.data_ptr() != exchange.grad.data_ptr():
+            raise RuntimeError("attack_sign_step_(exchange=...): spatial_rgb / grad must be the exchange's value / grad buffers")
+        exchange.attack_step(init.reshape(-1, 4).contiguous(), spatial_rgb.numel() // 4, step, eps, minimise)
+        return spatial_rgb
     if active_idx is not None:
         g = allreduce_active_rgb(grad, active_idx)
         rows, rows0 = spatial_rgb.reshape(-1, 4), init.reshape(-1, 4)
@@ -149,3 +157,216 @@ def attack_sign_step_(spatial_rgb: torch.Tensor, grad: torch.Tensor, init: torch
     rgb = torch.max(torch.min(rgb, init[..., :3] + eps), init[..., :3] - eps)
     spatial_rgb[..., :3] = rgb
     return spatial_rgb
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# exchange steps over NVLink peer memory (csrc/peer.cu): reduce-scatter + update + all-gather in ONE kernel per GPU
+# ------------------------------------------------------------------------------------------------------------------
+class _DeviceMemory:
+    """Raw device memory as a torch tensor without a copy (torch.as_tensor consumes __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n_floats: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerExchange:
+    """Symmetric (gradient, value, flags) buffers of the ranks of ONE node and the fused exchange kernels on them.
+
+    Every rank allocates its buffers with nfb_peer_alloc, publishes CUDA IPC handles through the process group
+    (all_gather_object — gloo or NCCL, host plumbing only) and opens the peers' buffers; afterwards no NCCL call is on the
+    data path: `attack_step` / `adam_step` are one kernel per GPU that reads the peers' gradients and writes the peers'
+    values through NVLink (csrc/peer.cu).  `grad` and `value` are this rank's buffers as flat fp32 tensors: accumulate the
+    local gradient into `grad`, keep the replicated quantity (perturbation table / flat parameters) in `value`.
+    With one rank the same kernels run without any peer traffic, so single-GPU code takes the same path."""
+
+    def __init__(self, n_grad: int, n_value: int, device=None, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        lib = _lib.load()
+        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.rank, self.world = world() if group is None else (dist.get_rank(group), dist.get_world_size(group))
+        if self.world > 8:
+            raise RuntimeError("PeerExchange spans the GPUs of one node (at most 8 ranks)")
+        pad4 = lambda n: (int(n) + 3) // 4 * 4
+        self.n_grad, self.n_value = pad4(n_grad), pad4(n_value)
+        sizes = (self.n_grad * 4, self.n_value * 4, int(lib.nfb_peer_flag_bytes()))
+        self._local, handles = [], []
+        with torch.cuda.device(self.device):
+            for nbytes in sizes:
+                p = C.c_void_p()
+                _lib.check(lib.nfb_peer_alloc(nbytes, C.byref(p)), "nfb_peer_alloc")
+                self._local.append(p.value)
+                h = C.create_string_buffer(64)
+                _lib.check(lib.nfb_peer_export(p, h), "nfb_peer_export")
+                handles.append(h.raw)
+            everyone = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(everyone, (self.rank, handles), group=group)
+            else:
+                everyone = [(0, handles)]
+            self._opened = []
+            table = [[None] * self.world for _ in range(3)]
+            for r, hs in everyone:
+                for k in range(3):
+                    if r == self.rank:
+                        table[k][r] = self._local[k]
+                    else:
+                        q = C.c_void_p()
+                        _lib.check(lib.nfb_peer_import(C.create_string_buffer(hs[k], 64), C.byref(q)), "nfb_peer_import")
+                        self._opened.append(q.value)
+                        table[k][r] = q.value
+            arrs = [(C.c_void_p * self.world)(*table[k]) for k in range(3)]
+            h = C.c_void_p()
+            _lib.check(lib.nfb_peer_create(C.byref(h), self.rank, self.world, arrs[0], arrs[1], arrs[2]), "nfb_peer_create")
+            self._h = h
+            self.grad = torch.as_tensor(_DeviceMemory(self._local[0], self.n_grad), device=self.device)
+            self.value = torch.as_tensor(_DeviceMemory(self._local[1], self.n_value), device=self.device)
+        if self.world > 1:
+            dist.barrier(group=group)           # every rank has opened every buffer before anyone launches
+
+    def status(self) -> None:
+        """Raises if a flag wait of an exchange kernel that has finished timed out (no synchronisation)."""
+        self._lib.check(self._lib.load().nfb_peer_status(self._h), "nfb_peer_status")
+
+    def attack_step(self, init: torch.Tensor, n_rows: int, step: float, eps: float, minimise: bool = True) -> None:
+        """attack_NeRFail_S.py:348-392 for this iteration: `grad` [n_rows,4] summed over ranks, sign step on the rows of
+        `value` [n_rows,4] with A > 0, clamped to init +- eps; every rank's `value` is updated, `grad` may be zeroed after."""
+        assert n_rows * 4 <= self.n_grad and n_rows * 4 <= self.n_value and init.is_contiguous() and init.numel() == n_rows * 4
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.load().nfb_attack_exchange_step(self._h, self._lib.ptr(init), n_rows,
+                                                                      float(step if minimise else -step), float(eps),
+                                                                      self._lib.stream()), "nfb_attack_exchange_step")
+
+    def adam_step(self, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, n: int, step_scalars: torch.Tensor, betas, eps: float,
+                  grad_scale: float) -> None:
+        """run_nerf.py:791-792 for this step: `grad` [n] averaged over ranks (grad_scale = 1 / world), Adam on this rank's
+        slice (the optimiser state is sharded), the new parameters written into every rank's `value` [n]."""
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.load().nfb_adam_exchange_step(self._h, self._lib.ptr(exp_avg), self._lib.ptr(exp_avg_sq), n,
+                                                                    self._lib.ptr(step_scalars), float(betas[0]), float(betas[1]),
+                                                                    float(eps), float(grad_scale), self._lib.stream()),
+                            "nfb_adam_exchange_step")
+
+    def close(self) -> None:
+        lib = self._lib.load()
+        if getattr(self, "_h", None):
+            torch.cuda.synchronize(self.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier()                  # nobody unmaps memory a peer's kernel may still touch
+            lib.nfb_peer_destroy(self._h)
+            self._h = None
+            for p in self._opened:
+                lib.nfb_peer_close(p)
+            self.grad = self.value = None
+            for p in self._local:
+                lib.nfb_peer_free(p)
+            self._opened, self._local = [], []
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self.world == 1:
+                self.close()
+        except Exception:
+            pass
+
+
+def shard_pixels(n_views: int, pixels_per_view: int, rank: int, world_size: int, quantum: int = 1):
+    """Balanced split of a batch of views by PIXELS rather than whole views (100 views over 8 ranks: 12.5 views each
+    instead of 13 / 12): [(view, pixel_begin, pixel_end)] of this rank, contiguous in (view, pixel) order.  The GaussNet
+    kernels are per pixel, so a rank can take part of a view (its rows); `quantum` keeps cuts on multiples of e.g. a row."""
+    total = n_views * pixels_per_view
+    units = total // quantum
+    b, e = shard_range(units, rank, world_size)
+    b, e = b * quantum, (e * quantum if rank < world_size - 1 else total)
+    out = []
+    v = b // pixels_per_view
+    while b < e:
+        end = min(e, (v + 1) * pixels_per_view)
+        out.append((v, b - v * pixels_per_view, end - v * pixels_per_view))
+        b, v = end, v + 1
+    return out
+
+
+class PeerAdam:
+    """Data-parallel optimiser step of NeRF retraining as ONE kernel per GPU (csrc/peer.cu: adam_exchange_kernel).
+
+    Replaces `all_reduce(grads) ; optimizer.step()` (a data-parallel run_nerf.py:791-792): the parameters of the networks
+    are re-pointed into a flat buffer in NVLink peer memory (state_dict order, coarse network first), the fused training
+    backward accumulates its flat gradient straight into the matching peer buffer (`net._grad_sink`), and `step()` lets
+    every GPU average ITS 1/G slice of the gradients over the peers, run Adam on it (exp_avg / exp_avg_sq are sharded: a
+    rank only ever touches its slice) and write the new parameters into every rank's copy.  No NCCL call, no replicated
+    full-size Adam.  `optimizer` (nerfail_b200.optim.Adam over the same parameters) keeps providing lr, betas, the step
+    count and the device-resident step scalars (graph mode), so learning-rate decay and CUDA-graph replay work as before;
+    `state_for_checkpoint()` gathers the sharded moments back into torch.optim.Adam's state_dict layout."""
+
+    def __init__(self, nets, optimizer, device=None, group=None):
+        self.nets = [n for n in nets if n is not None]
+        self.optimizer = optimizer
+        params = [p for n in self.nets for p in n.ordered_params()]
+        opt_params = [p for g in optimizer.param_groups for p in g["params"]]
+        if len(opt_params) != len(params) or any(a is not b for a, b in zip(params, opt_params)):
+            raise RuntimeError("PeerAdam: the optimizer must hold exactly the networks' parameters in state_dict order")
+        self.device = torch.device(device if device is not None else params[0].device)
+        self.n = sum(p.numel() for p in params)
+        self.ex = PeerExchange(self.n, self.n, self.device, group)
+        self.world = self.ex.world
+        self.m = torch.zeros(self.ex.n_value, dtype=torch.float32, device=self.device)
+        self.v = torch.zeros(self.ex.n_value, dtype=torch.float32, device=self.device)
+        off = 0
+        with torch.no_grad():
+            for net in self.nets:
+                begin = off
+                for p in net.ordered_params():
+                    k = p.numel()
+                    self.ex.value[off:off + k].copy_(p.data.reshape(-1))
+                    st = optimizer.state.get(p, {})
+                    if "exp_avg" in st:                      # resume: take over the moments the optimizer already holds
+                        self.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                        self.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    p.data = self.ex.value[off:off + k].view(p.shape)
+                    off += k
+                net._grad_sink = self.ex.grad[begin:off]
+                net.invalidate_fused()
+        self.params = params
+        optimizer.enable_graph_mode(self.device)
+
+    def step(self, begin: bool = True) -> None:
+        """After loss.backward(): average, Adam, broadcast.  begin=False when the caller (GraphedTrainStep) has already
+        advanced the optimizer's step count and uploaded this step's scalars (optimizer.begin_step())."""
+        if begin:
+            self.optimizer.begin_step()
+        g = self.optimizer.param_groups[0]
+        self.ex.adam_step(self.m, self.v, self.n, self.optimizer._dyn[0], g["betas"], g["eps"], 1.0 / self.world)
+        for p in self.params:
+            torch.autograd.graph.increment_version(p)
+
+    def state_for_checkpoint(self) -> dict:
+        """torch.optim.Adam state_dict with the full moments (each rank contributes its slice; collective)."""
+        m, v = self.m.clone(), self.v.clone()
+        if self.world > 1:
+            n4 = (self.n + 3) // 4
+            per = (n4 + self.world - 1) // self.world * 4
+            own = torch.zeros_like(m)
+            b, e = per * self.ex.rank, min(self.ex.n_value, per * (self.ex.rank + 1))
+            own[b:e] = m[b:e]
+            dist.all_reduce(own); m = own
+            own = torch.zeros_like(v); own[b:e] = v[b:e]
+            dist.all_reduce(own); v = own
+        off = 0
+        for p in self.params:
+            st = self.optimizer.state[p]
+            k = p.numel()
+            st["exp_avg"], st["exp_avg_sq"] = m[off:off + k].view(p.shape).clone(), v[off:off + k].view(p.shape).clone()
+            off += k
+        return self.optimizer.state_dict()
+
+    def close(self) -> None:
+        """Gives the parameters their own storage back and releases the peer memory."""
+        with torch.no_grad():
+            for p in self.params:
+                p.data = p.data.clone()
+        for n in self.nets:
+            n._grad_sink = None
+            n.invalidate_fused()
+        self.ex.close()

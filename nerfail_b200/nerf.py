@@ -132,6 +132,19 @@ class NeRF(nn.Module):
                   self.feature_linear.weight, self.feature_linear.bias,
                   self.alpha_linear.weight, self.alpha_linear.bias,
                   self.rgb_linear.weight, self.rgb_linear.bias]
+        first = parts[0]
+        if first.dtype == torch.float32 and first.is_contiguous():
+            # parameters that already lie back to back in one buffer (dist.PeerAdam re-points them into peer memory in
+            # exactly this order) are handed to the pack kernel as they are: no concatenation copy
+            base, off, ok = first.untyped_storage().data_ptr(), first.storage_offset(), True
+            for p in parts:
+                if (p.untyped_storage().data_ptr() != base or p.storage_offset() != off or not p.is_contiguous()
+                        or p.dtype != torch.float32):
+                    ok = False
+                    break
+                off += p.numel()
+            if ok:
+                return torch.as_strided(first.detach(), (off - first.storage_offset(),), (1,), first.storage_offset())
         return torch.cat([p.detach().reshape(-1).float() for p in parts])
 
     def ordered_params(self):

@@ -48,8 +48,9 @@ def get_ray_batch(H: int, W: int, K, c2w, near: float, far: float, device=None) 
     return rays
 
 
-def coarse_z(rays: torch.Tensor, n_samples: int, lindisp: bool = False, t_rand: Optional[torch.Tensor] = None):
-    """z_vals [R, n_samples] (run_nerf.py:357-379)."""
+def coarse_z(rays: torch.Tensor, n_samples: int, lindisp: bool = False, t_rand: Optional[torch.Tensor] = None,
+             rng: Optional[tuple] = None):
+    """z_vals [R, n_samples] (run_nerf.py:357-379).  rng = (seed, offset): stratified jitter drawn in the kernel (Philox)."""
     _require_cuda(rays, t_rand)
     rays = _f32(rays)
     assert rays.shape[1] >= 8
@@ -63,8 +64,12 @@ def coarse_z(rays: torch.Tensor, n_samples: int, lindisp: bool = False, t_rand: 
         t_rand = _f32(t_rand)
         assert t_rand.shape == (R, n_samples)
     with torch.cuda.device(rays.device):
-        check(_lib.load().nfb_coarse_z(ptr(rays), R, n_samples, int(bool(lindisp)), ptr(t_rand), ptr(z), stream()),
-              "nfb_coarse_z")
+        if rng is not None and t_rand is None:
+            check(_lib.load().nfb_coarse_z_rng(ptr(rays), R, n_samples, int(bool(lindisp)), int(rng[0]), int(rng[1]), ptr(z),
+                                               stream()), "nfb_coarse_z_rng")
+        else:
+            check(_lib.load().nfb_coarse_z(ptr(rays), R, n_samples, int(bool(lindisp)), ptr(t_rand), ptr(z), stream()),
+                  "nfb_coarse_z")
     return z
 
 
@@ -163,8 +168,9 @@ def sample_pdf(bins, weights, n_samples, u=None, return_inds=False):
     return (out, inds) if return_inds else out
 
 
-def hierarchical(z_coarse, weights, n_importance, u=None):
-    """(z_fine [R,Sc+N] ascending, z_samples [R,N], z_std [R]) — run_nerf.py:392-396, :412."""
+def hierarchical(z_coarse, weights, n_importance, u=None, rng: Optional[tuple] = None):
+    """(z_fine [R,Sc+N] ascending, z_samples [R,N], z_std [R]) — run_nerf.py:392-396, :412.  rng = (seed, offset): u drawn in
+    the kernel (Philox) instead of read from HBM."""
     _require_cuda(z_coarse, weights, u)
     z_coarse, weights = _f32(z_coarse), _f32(weights)
     R, Sc = z_coarse.shape
@@ -177,8 +183,12 @@ def hierarchical(z_coarse, weights, n_importance, u=None):
     z_samples = torch.empty((R, n_importance), dtype=torch.float32, device=dev)
     z_std = torch.empty((R,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().nfb_hierarchical(ptr(z_coarse), ptr(weights), ptr(u), R, Sc, n_importance, ptr(z_fine),
-                                           ptr(z_samples), ptr(z_std), stream()), "nfb_hierarchical")
+        if rng is not None and u is None:
+            check(_lib.load().nfb_hierarchical_rng(ptr(z_coarse), ptr(weights), int(rng[0]), int(rng[1]), R, Sc, n_importance,
+                                                   ptr(z_fine), ptr(z_samples), ptr(z_std), stream()), "nfb_hierarchical_rng")
+        else:
+            check(_lib.load().nfb_hierarchical(ptr(z_coarse), ptr(weights), ptr(u), R, Sc, n_importance, ptr(z_fine),
+                                               ptr(z_samples), ptr(z_std), stream()), "nfb_hierarchical")
     return z_fine, z_samples, z_std
 
 
@@ -559,8 +569,30 @@ class GaussGatherFn(torch.autograd.Function):
         return g, None, None, None, None
 
 
+def philox_uniform(seed: int, offset: int, stream_id: int, n: int, device=None) -> torch.Tensor:
+    """The n uniform numbers of Philox stream `stream_id` that the kernel-side draws consume (nfb_philox_uniform)."""
+    out = torch.empty(n, dtype=torch.float32, device=torch.device(device if device is not None else "cuda"))
+    with torch.cuda.device(out.device):
+        check(_lib.load().nfb_philox_uniform(int(seed), int(offset), int(stream_id), n, ptr(out), stream()), "nfb_philox_uniform")
+    return out
+
+
+_philox_state = {"seed": None, "offset": 0}
+
+
+def next_philox(device=None) -> tuple:
+    """(seed, offset) for one kernel-side draw: the seed is torch's (so torch.manual_seed makes renders reproducible), the
+    offset counts this process's draws since that seed was set."""
+    seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    if _philox_state["seed"] != seed:
+        _philox_state["seed"], _philox_state["offset"] = seed, 0
+    _philox_state["offset"] += 1
+    return seed, _philox_state["offset"]
+
+
 def render_rays_fused(coarse: "FusedMLP", fine: Optional["FusedMLP"], rays: torch.Tensor, N_samples: int, N_importance: int,
-                      lindisp: bool, white_bkgd: bool, t_rand=None, u=None, want_pts_max: bool = False) -> dict:
+                      lindisp: bool, white_bkgd: bool, t_rand=None, u=None, want_pts_max: bool = False,
+                      rng: Optional[tuple] = None) -> dict:
     """nfb_render_rays_fwd: the whole no-grad kernel sequence of render_rays (run_nerf.py:308-418) for one ray batch in one
     C call (coarse depths, fused MLP, compositing, resampling + merge, fused MLP, compositing [+ pts_max])."""
     lib = _lib.load()
@@ -583,6 +615,7 @@ def render_rays_fused(coarse: "FusedMLP", fine: Optional["FusedMLP"], rays: torc
     with torch.cuda.device(dev):
         check(lib.nfb_render_rays_fwd(coarse._h, fine._h if fine is not None else None, ptr(rays), R, N_samples, N_importance,
                                       int(bool(lindisp)), int(bool(white_bkgd)), ptr(t_rand), ptr(u),
+                                      int(rng is not None), int(rng[0]) if rng else 0, int(rng[1]) if rng else 0,
                                       ptr(out["rgb_map"]), ptr(out["disp_map"]), ptr(out["acc_map"]),
                                       ptr(out.get("rgb0")), ptr(out.get("disp0")), ptr(out.get("acc0")), ptr(out.get("z_std")),
                                       ptr(out.get("pts_max")), ptr(ws), nbytes, stream()), "nfb_render_rays_fwd")
@@ -629,6 +662,132 @@ class ChwToRgbaFn(torch.autograd.Function):
         with torch.cuda.device(gg.device):
             check(_lib.load().nfb_rgba_to_chw(ptr(gg), None, ptr(alpha_src), B, H * W, 0.0, ptr(out), stream()), "nfb_rgba_to_chw")
         return out, None
+
+
+# ---- classifier input with the bilinear Resize fused behind the RGBA -> CHW conversion (GaussNet.py:121-154) ----
+_resize_tables = {}
+
+
+def resize_tables(in_size: int, out_size: int, antialias: bool, transposed: bool, device):
+    """(start int32 [n], count int32 [n], weights fp32 [n, maxk], maxk) of one axis on `device`, cached: the separable
+    bilinear resampling of torchvision Resize / ATen upsample_bilinear2d(_aa), computed on the host by nfb_resize_weights."""
+    device = torch.device(device)
+    key = (in_size, out_size, bool(antialias), bool(transposed), device.type, device.index)
+    hit = _resize_tables.get(key)
+    if hit is not None:
+        return hit
+    lib = _lib.load()
+    maxk = int(lib.nfb_resize_max_taps(in_size, out_size, int(antialias), int(transposed)))
+    n = in_size if transposed else out_size
+    start, count = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    w = np.zeros((n, maxk), np.float32)
+    check(lib.nfb_resize_weights(in_size, out_size, int(antialias), int(transposed), maxk, start.ctypes.data, count.ctypes.data,
+                                 w.ctypes.data), "nfb_resize_weights")
+    hit = (torch.from_numpy(start).to(device), torch.from_numpy(count).to(device), torch.from_numpy(w).to(device), maxk)
+    _resize_tables[key] = hit
+    return hit
+
+
+def default_resize_antialias() -> bool:
+    """What `torchvision.transforms.Resize([s, s])` does to a float tensor in the torchvision that is installed: antialias
+    defaults to True from 0.17 on; the 0.15 the reference pins (README.md:56) warns and does NOT antialias tensors.
+    NERFAIL_B200_RESIZE_ANTIALIAS=0/1 overrides."""
+    env = os.environ.get("NERFAIL_B200_RESIZE_ANTIALIAS")
+    if env is not None:
+        return env == "1"
+    try:
+        import torchvision
+        major, minor = (int(v) for v in torchvision.__version__.split(".")[:2])
+        return (major, minor) >= (0, 17)
+    except Exception:
+        return True
+
+
+def _rgba_to_chw_resized(img_f32, img_u8, alpha_src, alpha_batch, B, H, W, size, fill, antialias):
+    src = img_f32 if img_f32 is not None else img_u8
+    dev = src.device
+    ys, yc, yw, yk = resize_tables(H, size, antialias, False, dev)
+    xs, xc, xw, xk = resize_tables(W, size, antialias, False, dev)
+    out = torch.empty((B, 3, size, size), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().nfb_rgba_to_chw_resized(ptr(img_f32), ptr(img_u8), ptr(alpha_src), alpha_batch, B, H, W, size, size,
+                                                  float(fill), ptr(ys), ptr(yc), ptr(yw), yk, ptr(xs), ptr(xc), ptr(xw), xk,
+                                                  ptr(out), stream()), "nfb_rgba_to_chw_resized")
+    return out
+
+
+def chw_resized_to_rgba(g_out: torch.Tensor, alpha_src: torch.Tensor, H: int, W: int, antialias: bool) -> torch.Tensor:
+    """Adjoint of the fused conversion + resize: g_out [NB,3,S,S] -> g_img [NB,H,W,4]; alpha_src [B,H,W,4] with NB a multiple
+    of B (cotangent n uses image n % B — NC class gradients of the same B images in one launch)."""
+    g_out = _f32(g_out)
+    NB, _, S, _ = g_out.shape
+    Bm = alpha_src.shape[0]
+    assert NB % Bm == 0
+    dev = g_out.device
+    ys, yc, yw, yk = resize_tables(H, S, antialias, True, dev)
+    xs, xc, xw, xk = resize_tables(W, S, antialias, True, dev)
+    g_img = torch.empty((NB, H, W, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().nfb_chw_resized_to_rgba(ptr(g_out), ptr(alpha_src), Bm, NB, H, W, S, S, ptr(ys), ptr(yc), ptr(yw), yk,
+                                                  ptr(xs), ptr(xc), ptr(xw), xk, ptr(g_img), stream()), "nfb_chw_resized_to_rgba")
+    return g_img
+
+
+class RgbaToChwResizedFn(torch.autograd.Function):
+    """[B,H,W,4] RGBA -> [B,3,S,S]: white where alpha == 0, NCHW, bilinear Resize([S,S]) — one kernel (GaussNet.py:121-154).
+    Backward = ChwResizedToRgbaFn (the adjoint gather), whose backward is this op with fill 0: differentiable twice."""
+
+    @staticmethod
+    def forward(ctx, img, fill, size, antialias):
+        img = _f32(img)
+        B, H, W, _ = img.shape
+        ctx.save_for_backward(img)
+        ctx.antialias = antialias
+        return _rgba_to_chw_resized(img, None, None, 1, B, H, W, size, fill, antialias)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (img,) = ctx.saved_tensors
+        return ChwResizedToRgbaFn.apply(g_out, img, ctx.antialias), None, None, None
+
+
+class ChwResizedToRgbaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g_out, alpha_src, antialias):
+        ctx.save_for_backward(alpha_src)
+        ctx.antialias, ctx.size = antialias, g_out.shape[-1]
+        return chw_resized_to_rgba(g_out, alpha_src, alpha_src.shape[1], alpha_src.shape[2], antialias)
+
+    @staticmethod
+    def backward(ctx, gg_img):
+        (alpha_src,) = ctx.saved_tensors
+        gg = _f32(gg_img)
+        B, H, W, _ = gg.shape
+        return _rgba_to_chw_resized(gg, None, alpha_src, alpha_src.shape[0], B, H, W, ctx.size, 0.0, ctx.antialias), None, None
+
+
+def rgba_u8_to_chw_resized(img_u8: torch.Tensor, size: int, antialias: bool, fill: float = 255.0) -> torch.Tensor:
+    """The same for the original uint8 image (no gradient)."""
+    img_u8 = img_u8.contiguous()
+    B, H, W, _ = img_u8.shape
+    return _rgba_to_chw_resized(None, img_u8, None, 1, B, H, W, size, fill, antialias)
+
+
+def gauss_scatter_bwd_batched(g_xrgba, x, w_idx, ori_u8, eps, table_shape):
+    """[NC,B,H,W,4] cotangents of x_rgba -> [NC,*table_shape] gradients w.r.t. the perturbation table in one launch
+    (nfb_gauss_scatter_bwd_batched: DeepFool's per-class gradients, deepfool.py:72-86)."""
+    g_xrgba = _f32(g_xrgba)
+    NC = g_xrgba.shape[0]
+    T = int(np.prod(table_shape)) // 4
+    B = w_idx.shape[0]
+    HW = w_idx.shape[2] * w_idx.shape[3]
+    assert g_xrgba.numel() == NC * B * HW * 4
+    g_table = torch.zeros((NC,) + tuple(table_shape), dtype=torch.float32, device=w_idx.device)
+    with torch.cuda.device(w_idx.device):
+        check(_lib.load().nfb_gauss_scatter_bwd_batched(ptr(g_xrgba), NC, ptr(x), ptr(w_idx), ptr(ori_u8), B, HW,
+                                                        -1.0 if eps is None else float(eps), T, ptr(g_table), stream()),
+              "nfb_gauss_scatter_bwd_batched")
+    return g_table
 
 
 def rgba_u8_to_chw(img_u8: torch.Tensor, fill: float = 255.0) -> torch.Tensor:
@@ -707,7 +866,7 @@ class FusedMLPTrainFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(lib.nfb_mlp_fwd_train(fused._h, ptr(rays), ptr(z_vals), R, S, ptr(raw), ptr(act), ptr(mask), stream()),
                   "nfb_mlp_fwd_train")
-        ctx.fused, ctx.M, ctx.T = fused, M, T
+        ctx.fused, ctx.M, ctx.T, ctx.net = fused, M, T, net
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.n_params = sum(math.prod(sh) for sh in ctx.shapes)
         ctx.save_for_backward(act, mask)
@@ -721,7 +880,12 @@ class FusedMLPTrainFn(torch.autograd.Function):
         dev = act.device
         g_raw = _f32(g_raw).reshape(M, 4)
         dy = torch.empty((T, 39, 128, 64), dtype=torch.bfloat16, device=dev)
-        grad = torch.zeros(ctx.n_params, dtype=torch.float32, device=dev)
+        sink = getattr(ctx.net, "_grad_sink", None)
+        if sink is not None:        # data-parallel: the flat gradient lives in NVLink peer memory (dist.PeerAdam)
+            grad = sink
+            grad.zero_()
+        else:
+            grad = torch.zeros(ctx.n_params, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             if os.environ.get("NERFAIL_B200_BWD", "serial") != "overlap":
                 check(lib.nfb_mlp_bwd_data(ctx.fused._h, ptr(g_raw), M, ptr(mask), ptr(dy), stream()), "nfb_mlp_bwd_data")

@@ -115,3 +115,131 @@ def build_attack_inputs(H: int, W: int, K, base_poses, view_poses, render_kwargs
             save_index_and_dist(os.path.join(save_dir, "index_and_dist", f"{i}.pth"), di)
             save_index_and_weight(os.path.join(save_dir, "index_and_weight", f"{i}.pth"), iw)
     return sps, torch.stack(out, 0)
+
+
+# ---- asynchronous file output shared by the sweep drivers ------------------------------------------------------
+class _AsyncWriter:
+    """Device results leave through a ring of pinned host buffers on a side stream; encoding / torch.save / cv2.imwrite run
+    on a writer thread (they release the GIL), so the launch loop never waits for the disk.  `put(tensor, fn)` copies the
+    tensor and later calls fn(host_numpy_or_tensor) on the thread; close() joins and re-raises the first error."""
+
+    def __init__(self, device, depth: int = 4):
+        import queue
+        import threading
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self.free = threading.Semaphore(depth)
+        self.q = queue.Queue()
+        self.err = None
+        self.thread = threading.Thread(target=self._drain, daemon=True)
+        self.thread.start()
+
+    def put(self, t: torch.Tensor, fn) -> None:
+        self.free.acquire()
+        host = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            host.copy_(t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.q.put((host, done, fn, t))                  # t stays referenced until the copy has finished
+
+    def _drain(self):
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            host, done, fn, _keep = job
+            try:
+                done.synchronize()
+                fn(host)
+            except Exception as e:                       # surfaced by close()
+                if self.err is None:
+                    self.err = e
+            finally:
+                self.free.release()
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+        if self.err is not None:
+            raise self.err
+
+
+def knn_sweep(view_points: Sequence, base, out_dir: Optional[str] = None, rank: Optional[int] = None,
+              world_size: Optional[int] = None, c: float = GAUSS_C, keep: bool = True):
+    """The 8-NN precompute over all views of a data set (create_index_and_dist.py:110-163, then tools/dist_to_weight.py:80-97),
+    SHARDED BY QUERY VIEW: rank r answers the views i with i % world_size == r against the replicated base points (23 MB for
+    P = 3) — views are independent, there is no collective.  `view_points[i]` is a [H,W,3] tensor or the path
+    of the view's NNN.npy; `base` a SpatialPointSet, a [P,H,W,3] tensor, or the list of the P base views' .npy paths.
+    With out_dir every rank writes index_and_dist/<i>.pth and index_and_weight/<i>.pth in the reference's format through an
+    asynchronous writer, the ranks of a node filling one directory like the reference's single process.
+    Returns [(i, index_and_weight [2,H,W,8])] of this rank (empty tensors list if keep=False)."""
+    from . import dist as nd
+    r, w = nd.world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if isinstance(base, SpatialPointSet):
+        sps = base
+    elif isinstance(base, torch.Tensor):
+        sps = SpatialPointSet(base.to(dev), c)
+    else:
+        sps = SpatialPointSet.from_npy(list(base), dev, c)
+    writer = None
+    if out_dir is not None:
+        for sub in ("index_and_dist", "index_and_weight"):
+            os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
+        writer = _AsyncWriter(dev)
+    out = []
+    try:
+        for i in nd.shard_views(len(view_points), rank, world_size):
+            v = view_points[i]
+            pts = load_points_npy(v, dev) if isinstance(v, (str, os.PathLike)) else v.to(dev, torch.float32)
+            di = sps.index_and_dist(pts)
+            iw = ops.gauss_weights(di.unsqueeze(0), sps.c)[0]
+            if writer is not None:
+                writer.put(di, lambda h, p=os.path.join(out_dir, "index_and_dist", f"{i}.pth"): torch.save(h.clone(), p))
+                writer.put(iw, lambda h, p=os.path.join(out_dir, "index_and_weight", f"{i}.pth"): torch.save(h.clone(), p))
+            if keep:
+                out.append((i, iw))
+    finally:
+        if writer is not None:
+            writer.close()
+    return out
+
+
+class AttackImageSink:
+    """The image output of the attack's last epoch (attack_NeRFail_S.py:394-403: per view `cv2.imwrite` of the perturbed RGBA
+    image x_rgba, of the un-composited perturbation x and of the original, each a blocking `.cpu().detach().numpy()` + PNG
+    encode on the attack's only thread) as an asynchronous sink: the float images are converted to the uint8 PNG payload on
+    the device with cv2's own rule for float input (saturate_cast: round half to even, clamp to [0, 255]), cross PCIe at a
+    quarter of the size, and are encoded on the writer thread.  Files are byte-identical to the reference's."""
+
+    def __init__(self, device=None, depth: int = 6):
+        dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.writer = _AsyncWriter(dev, depth)
+
+    @staticmethod
+    def _payload(img: torch.Tensor) -> torch.Tensor:
+        if img.dtype == torch.uint8:
+            return img.contiguous()
+        return torch.round(img.detach().float()).clamp_(0, 255).to(torch.uint8)
+
+    def put(self, x_rgba: torch.Tensor, x: torch.Tensor, ori_img: torch.Tensor, img_names: Sequence[str],
+            mask_names: Sequence[str]) -> None:
+        """One batch: x_rgba / x / ori_img [B,H,W,4]; img_names / mask_names as the reference's dataset yields them."""
+        import cv2
+        for b, (name, mname) in enumerate(zip(img_names, mask_names)):
+            for t, path in ((x_rgba[b], name), (x[b], mname), (ori_img[b], name.replace(".png", "_ori.png"))):
+                self.writer.put(self._payload(t), lambda h, p=path: cv2.imwrite(p, h.numpy()))
+
+    def close(self) -> None:
+        self.writer.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -126,11 +126,19 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             and 3 <= N_samples <= 128 and N_samples + N_importance <= 512
             and os.environ.get("NERFAIL_B200_RENDER_RAYS", "fused") != "ops"):
         dev = ray_batch.device
-        t_r = torch.rand((N_rays, N_samples), device=dev) if perturb > 0. else None
-        u_r = torch.rand((N_rays, N_importance), device=dev) if (perturb != 0. and N_importance > 0) else None
+        t_r = u_r = rng = None
+        if perturb != 0.:
+            # stratified draws: Philox inside the kernels (no [R,64] + [R,128] HBM tensors, no torch.rand launches) unless
+            # NERFAIL_B200_RNG=torch asks for torch's generator (what the per-op path and autograd use).  The reference
+            # jitters the coarse depths for perturb > 0 (:365) and draws u for perturb != 0 (:393, det = perturb == 0).
+            if os.environ.get("NERFAIL_B200_RNG", "philox") == "torch" or perturb < 0.:
+                t_r = torch.rand((N_rays, N_samples), device=dev) if perturb > 0. else None
+                u_r = torch.rand((N_rays, N_importance), device=dev) if N_importance > 0 else None
+            else:
+                rng = ops.next_philox()
         fine = network_fine.fused() if network_fine is not None else None
         return ops.render_rays_fused(network_fn.fused(), fine, ray_batch, N_samples, N_importance, lindisp, white_bkgd,
-                                     t_r, u_r, want_pts_max=with_pts_max)
+                                     t_r, u_r, want_pts_max=with_pts_max, rng=rng)
     t_rand = None
     if perturb > 0.:
         if pytest:

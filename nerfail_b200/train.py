@@ -86,10 +86,12 @@ def _poll_networks(kw: dict) -> None:
 
 def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwargs_train: dict, optimizer,
                lrate: float, lrate_decay: int, global_step: int, near: Optional[float] = None,
-               far: Optional[float] = None) -> dict:
+               far: Optional[float] = None, exchange=None, _begun: bool = False) -> dict:
     """One optimisation step (run_nerf.py:776-800): render the batch with retraw, loss = mse(fine) + mse(coarse),
     backward, (data-parallel: all-reduce of the gradients, scale 1/G), optimizer.step(), exponential lr decay evaluated
-    at global_step like the reference.  Returns {'loss', 'psnr', 'psnr0'} as device scalars (no host sync)."""
+    at global_step like the reference.  Returns {'loss', 'psnr', 'psnr0'} as device scalars (no host sync).
+    exchange: a dist.PeerAdam over the same networks / optimizer — the gradient average, Adam and the parameter broadcast
+    then are one kernel per GPU over NVLink peer memory instead of two NCCL all-reduces and a replicated Adam."""
     kw = dict(render_kwargs_train)
     if near is not None:
         kw.update(near=near, far=far)
@@ -105,13 +107,16 @@ def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwarg
             out["psnr0"] = _psnr(img_loss0.detach())
         loss.backward()
     _, world_size = nd.world()
-    if world_size > 1:
-        nets = [kw.get("network_fn"), kw.get("network_fine")]
-        pending = [nd.allreduce_grads_(n.parameters(), scale=1.0 / world_size, async_op=True) for n in nets if n is not None]
-        for fin in pending:
-            if fin is not None:
-                fin()
-    optimizer.step()
+    if exchange is not None:
+        exchange.step(begin=not _begun)
+    else:
+        if world_size > 1:
+            nets = [kw.get("network_fn"), kw.get("network_fine")]
+            pending = [nd.allreduce_grads_(n.parameters(), scale=1.0 / world_size, async_op=True) for n in nets if n is not None]
+            for fin in pending:
+                if fin is not None:
+                    fin()
+        optimizer.step()
     set_lrate(optimizer, decayed_lrate(lrate, lrate_decay, global_step))
     _poll_networks(kw)
     out["loss"] = loss.detach()
@@ -128,7 +133,8 @@ class GraphedTrainStep:
     (optim.Adam.begin_step).  Same arithmetic as train_step; checked by test_graphed_train_step_equals_eager."""
 
     def __init__(self, n_rays: int, H: int, W: int, K, chunk: int, render_kwargs_train: dict, optimizer, lrate: float,
-                 lrate_decay: int, near: Optional[float] = None, far: Optional[float] = None, device=None, warmup: int = 3):
+                 lrate_decay: int, near: Optional[float] = None, far: Optional[float] = None, device=None, warmup: int = 3,
+                 exchange=None):
         self.device = torch.device(device if device is not None else "cuda")
         self.args = (H, W, K, chunk)
         self.kw, self.optimizer = render_kwargs_train, optimizer
@@ -136,6 +142,7 @@ class GraphedTrainStep:
         self.batch_rays = torch.zeros(2, n_rays, 3, device=self.device)
         self.target_s = torch.zeros(n_rays, 3, device=self.device)
         self.warmup = warmup
+        self.exchange = exchange           # dist.PeerAdam: fused average + Adam + broadcast over NVLink peer memory
         self.graph = None
         self.out = None
         optimizer.enable_graph_mode(self.device)
@@ -146,7 +153,7 @@ class GraphedTrainStep:
     def _eager(self, global_step):
         H, W, K, chunk = self.args
         return train_step(self.batch_rays, self.target_s, H, W, K, chunk, self.kw, self.optimizer, self.lrate,
-                          self.lrate_decay, global_step, self.near, self.far)
+                          self.lrate_decay, global_step, self.near, self.far, exchange=self.exchange, _begun=True)
 
     def __call__(self, batch_rays, target_s, global_step: int) -> dict:
         """One step on (batch_rays [2,n,3], target_s [n,3]); returns {'loss', 'psnr', 'psnr0'} (device scalars that the

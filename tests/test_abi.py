@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
-    assert _lib.load().nfb_abi_version() == 1
+    assert _lib.load().nfb_abi_version() == 2
 
 
 def test_error_reporting_without_compute():
@@ -86,3 +86,16 @@ def test_state_dict_keys_and_param_order_match_reference_layout():
 def _count():
     from nerfail_b200 import _lib
     return int(_lib.load().nfb_mlp_param_count(None))
+
+
+def test_philox_reference_known_answers():
+    """The numpy Philox4x32-10 that checks the kernel-side generator (tests/philox_ref.py) against the known-answer vectors
+    of the Random123 distribution (kat_vectors: philox4x32 10 rounds)."""
+    import numpy as np
+    from philox_ref import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10(*[np.array([c], np.uint64) for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want

@@ -83,3 +83,23 @@ def test_shard_range_is_a_partition():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_shard_pixels_is_a_balanced_partition():
+    """dist.shard_pixels: the (view, pixel range) pieces of all ranks tile the batch exactly once, in order, cut on the
+    quantum, and no rank has more than one quantum more than another (100 views over 8 ranks: 12.5 views each)."""
+    from nerfail_b200 import dist as nd
+    for V, px, q in ((100, 640000, 800), (100, 640000, 1), (3, 10, 1), (7, 24, 8), (1, 64, 16), (5, 30, 30)):
+        for w in (1, 2, 3, 4, 8):
+            pieces = [nd.shard_pixels(V, px, r, w, q) for r in range(w)]
+            flat = [p for ps in pieces for p in ps]
+            pos = 0
+            for v, b, e in flat:
+                assert 0 <= b < e <= px and v * px + b == pos, (V, px, q, w, v, b, e, pos)
+                pos = v * px + e
+            assert pos == V * px
+            loads = [sum(e - b for _, b, e in ps) for ps in pieces]
+            assert max(loads) - min(loads) <= q + (V * px) % q, (loads, q)
+            if q > 1:
+                assert all(b % q == 0 for _, b, _ in flat)
+    assert [sum(e - b for _, b, e in nd.shard_pixels(100, 640000, r, 8, 800)) for r in range(8)] == [8000000] * 8

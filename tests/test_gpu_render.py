@@ -391,6 +391,7 @@ def test_render_rays_single_call_equals_op_sequence(cuda, monkeypatch):
     the same kernels in the same order, so every output is bit-identical — deterministic and stratified sampling (same
     torch generator draws), with and without the fine network / pts_max, ragged batch sizes."""
     import nerfail_b200 as nb
+    monkeypatch.setenv("NERFAIL_B200_RNG", "torch")       # both sides draw from torch's generator (the fused path defaults to Philox)
     _, kw = make_kwargs(cuda)
     K, _ = synth.intrinsics(30, 30)
     rays = no.camera_rays(30, 30, K, torch.tensor(synth.pose_spherical(40.0, -30.0, 4.0)[:3, :4]), 2.0, 6.0).to(cuda)
