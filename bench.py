@@ -99,7 +99,12 @@ class LegoArgs:
 
 
 def cpu_reference_rays_per_s(n_rays: int, seed_c=0, seed_f=1):
-    """The oracle port of the reference render path (coarse + fine, chunk 1024) on the host cores."""
+    """The reference's own CPU implementation of the render path (coarse + fine, chunk 1024) on the host cores.
+    When oracle/_ref holds the staged, UNMODIFIED reference (oracle/make_ref.py) its run_nerf.render() is what runs —
+    the reference's public entry point with rays= , its own NeRF modules, embedders and network_query_fn as create_nerf
+    builds them (run_nerf.py:181-204) — kind "reference"; otherwise the oracle port, kind "port".
+    Returns (rays/s, seconds, threads, kind)."""
+    from oracle import make_ref
     from oracle import nerf_oracle as no
     from oracle import synth
     torch.set_num_threads(os.cpu_count() or 1)
@@ -109,12 +114,32 @@ def cpu_reference_rays_per_s(n_rays: int, seed_c=0, seed_f=1):
     rays = no.camera_rays(H, W, K, torch.tensor(synth.pose_spherical(30.0, -30.0, 4.0)[:3, :4]), 2.0, 6.0)
     g = torch.Generator().manual_seed(0)
     rays = rays[torch.randperm(rays.shape[0], generator=g)[:n_rays]]
+    if make_ref.available():
+        run_nerf, helpers = make_ref.ref_modules()
+        nets = []
+        for sd in (sd_c, sd_f):
+            n = helpers.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True)
+            n.load_state_dict(sd)
+            nets.append(n)
+        embed_fn, _ = helpers.get_embedder(10, 0)
+        embeddirs_fn, _ = helpers.get_embedder(4, 0)
+        query = lambda inputs, viewdirs, network_fn: run_nerf.run_network(inputs, viewdirs, network_fn, embed_fn=embed_fn,
+                                                                          embeddirs_fn=embeddirs_fn, netchunk=1024 * 64)
+        kw = dict(network_query_fn=query, perturb=False, N_importance=N_IMPORTANCE, network_fine=nets[1], N_samples=N_SAMPLES,
+                  network_fn=nets[0], use_viewdirs=True, white_bkgd=True, raw_noise_std=0., ndc=False, lindisp=False,
+                  near=2.0, far=6.0)
+        batch = (rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous())
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            run_nerf.render(H, W, K, chunk=CHUNK, rays=batch, **kw)
+        dt = time.perf_counter() - t0
+        return n_rays / dt, dt, torch.get_num_threads(), "reference"
     t0 = time.perf_counter()
     with torch.no_grad():
         for i in range(0, n_rays, CHUNK):
             no.render_ray_batch(rays[i:i + CHUNK], sd_c, sd_f, N_SAMPLES, N_IMPORTANCE, True)
     dt = time.perf_counter() - t0
-    return n_rays / dt, dt, torch.get_num_threads()
+    return n_rays / dt, dt, torch.get_num_threads(), "port"
 
 
 def run_reference(args):
@@ -124,12 +149,14 @@ def run_reference(args):
     n = 8192                                   # ~3.5 s of 16-core CPU work per step: K=5, W=3 stays under a minute
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_rays_per_s(256)
-    vals, cores = [], 1
+    vals, cores, kind = [], 1, "port"
     t_total = 0.0
     for _ in range(args.steps):
-        v, dt, cores = cpu_reference_rays_per_s(n)
+        v, dt, cores, kind = cpu_reference_rays_per_s(n)
         vals.append(v); t_total += dt
     value = n * args.steps / t_total
+    how = ("the unmodified reference's run_nerf.render() staged under oracle/_ref (oracle/make_ref.py)" if kind == "reference"
+           else "oracle/nerf_oracle.py (oracle/_ref absent)")
     line = {
         "impl": "reference", "metric": "render rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
@@ -137,8 +164,8 @@ def run_reference(args):
         "config": {"workload": "single 800x800 synthetic Blender view render (coarse+fine, 1024-ray chunks)",
                    "N_samples": N_SAMPLES, "N_importance": N_IMPORTANCE, "netwidth": 256, "multires": [10, 4],
                    "sample": f"{n} random rays of the view per step"},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{n} rays x {args.steps} steps, torch CPU fp32, oracle/nerf_oracle.py"},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind,
+                         "sample": f"{n} rays x {args.steps} steps, torch CPU fp32, {how}"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -163,23 +190,29 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
             return float(t)
         return ms
 
-    # ---- config 3: attack iteration (kernels + all-reduce) ----
+    # ---- config 3: attack iteration (gather + scatter over this rank's pixels, exchange + sign step) ----
     P, Hh, Ww, V = 3, 800, 800, 100
-    mine = nd.shard_views(V, rank, world)
+    HW = Hh * Ww
+    pieces = nd.shard_pixels(V, HW, rank, world, quantum=Ww)          # 100 views over 8 ranks: 12.5 views each, cut on rows
+    n_px = sum(e_ - b_ for _, b_, e_ in pieces)
     g = torch.Generator(device="cpu").manual_seed(1234)
-    table = torch.randn(P, Hh, Ww, 4, generator=g) * 5.0
+    table0 = torch.randn(P, Hh, Ww, 4, generator=g) * 5.0
     yy, xx = torch.meshgrid(torch.arange(Hh, dtype=torch.float32), torch.arange(Ww, dtype=torch.float32), indexing="ij")
     disc = ((yy - Hh / 2) ** 2 + (xx - Ww / 2) ** 2) <= 0.4 * Hh * Ww / np.pi          # A = 255 on a centred disc of ~40 % of the pixels
-    table[..., 3] = disc.float() * 255.0
-    table = table.to(dev).requires_grad_(True)
-    active_idx = nd.active_rows(table.detach())
-    T = P * Hh * Ww
+    table0[..., 3] = disc.float() * 255.0
+    T = P * HW
+    ex = nd.PeerExchange(T * 4, T * 4, dev)                        # perturbation table + its gradient in NVLink peer memory
+    table = ex.value[:T * 4].view(P, Hh, Ww, 4)
+    table.copy_(table0.to(dev))
+    init = table.clone()
+    grad = ex.grad[:T * 4].view(P, Hh, Ww, 4)
+    active_fraction = float((table0[..., 3] > 0).float().mean())
     VB = 10                                     # views per kernel launch (the reference attack batches 8, attack_NeRFail_S.py:81)
     gd = torch.Generator(device=dev).manual_seed(100 + rank)
-    base_idx = torch.arange(Hh * Ww, device=dev).reshape(1, Hh, Ww, 1)
+    base_idx = torch.arange(HW, device=dev).reshape(1, Hh, Ww, 1)
     batches = []
     for _ in range(2):                          # two distinct 10-view batches, cycled (820 MB of weights/indices)
-        idx = (base_idx + torch.randint(0, P, (VB, 1, 1, 1), device=dev, generator=gd) * Hh * Ww
+        idx = (base_idx + torch.randint(0, P, (VB, 1, 1, 1), device=dev, generator=gd) * HW
                + torch.randint(-400, 401, (VB, Hh, Ww, 8), device=dev, generator=gd)).clamp_(0, T - 1).float()
         dist_ = torch.sort(torch.randn(VB, Hh, Ww, 8, device=dev, generator=gd).abs() * 0.01, dim=-1).values
         w_idx = ops.gauss_weights(torch.stack([dist_, idx], 1), 0.02)
@@ -187,42 +220,74 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
         gx = torch.randn(VB, Hh, Ww, 4, device=dev, generator=gd)
         batches.append((w_idx, ori, gx))
         del idx, dist_
-    n_mine = len(mine)
+    full_views, rem_px = n_px // HW, n_px % HW
+    part = None
+    if rem_px:                                  # this rank's part of a view: rem_px / W rows as their own contiguous tensors
+        rr = rem_px // Ww
+        w0, o0, g0 = batches[0]
+        part = (w0[:1, :, :rr].contiguous(), o0[:1, :rr].contiguous(), g0[:1, :rr].contiguous())
+    tshape = (P, Hh, Ww, 4)
+
+    def scatter_views():
+        done, i = 0, 0
+        while done < full_views:
+            w_idx, ori, gx = batches[i % len(batches)]
+            nb_ = min(VB, full_views - done)
+            x, x_rgba = ops.gauss_gather_fwd(table.reshape(-1, 4), w_idx[:nb_], ori[:nb_], 32.0)
+            ops.gauss_scatter_bwd(None, gx[:nb_], x, w_idx[:nb_], ori[:nb_], 32.0, tshape, out=grad)
+            done += nb_; i += 1
+        if part is not None:
+            x, x_rgba = ops.gauss_gather_fwd(table.reshape(-1, 4), part[0], part[1], 32.0)
+            ops.gauss_scatter_bwd(None, part[2], x, part[0], part[1], 32.0, tshape, out=grad)
 
     def attack_iter():
-        grad = torch.zeros_like(table)
-        done, i = 0, 0
-        while done < n_mine:
-            w_idx, ori, gx = batches[i % len(batches)]
-            nb_ = min(VB, n_mine - done)
-            x, x_rgba = ops.gauss_gather_fwd(table.detach().reshape(-1, 4), w_idx[:nb_], ori[:nb_], 32.0)
-            ops.gauss_scatter_bwd(None, gx[:nb_], x, w_idx[:nb_], ori[:nb_], 32.0, table.shape, out=grad)
-            done += nb_; i += 1
-        # the whole table: at NVLink speed packing the 9.2 MB the sign step consumes (dist.allreduce_active_rgb: 0.93 ms per
-        # iteration at 8 GPUs) buys nothing over the 30.7 MB all-reduce (0.87-1.00 ms over three runs): latency-, not bandwidth-bound
-        nd.allreduce_sum_(grad)
-        return grad
+        # attack_NeRFail_S.py:317-392 minus the classifier: zero the gradient, forward + backward of this rank's pixels,
+        # then ONE kernel per GPU that sums the partial gradients over NVLink peer memory, takes the sign step on the rows it
+        # owns and writes them into every rank's table (csrc/peer.cu) - the I-FGSM update is inside the timed iteration
+        grad.zero_()
+        scatter_views()
+        ex.attack_step(init.reshape(-1, 4), T, 1.0, 8.0)
 
-    for _ in range(2):
-        attack_iter()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = ev(), ev()
-    iters = 3
-    e0.record()
-    for _ in range(iters):
-        attack_iter()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = sync_max(e0.elapsed_time(e1)) / iters
-    px = V * Hh * Ww
+    def attack_iter_nccl():
+        # the round-1 form for comparison: NCCL all-reduce of the whole gradient table, then the update as its own kernels
+        grad.zero_()
+        scatter_views()
+        nd.attack_sign_step_(table, grad, init, 1.0, 8.0)
+
+    def time_iters(fn, iters=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return sync_max(e0.elapsed_time(e1)) / iters
+
+    ms = time_iters(attack_iter)
+    ex.status()
+    ms_nccl = time_iters(attack_iter_nccl)
+    ms_local = time_iters(lambda: (grad.zero_(), scatter_views()))
+    px = V * HW
+    slice_rows = (T + world - 1) // world
+    nvlink_bytes = int(active_fraction * slice_rows * 16 * (world - 1))
     out["attack_iteration"] = {"metric": "GaussNet fwd+bwd attack rays/s (1 pixel = 1 ray)", "value": px / (ms / 1e3), "unit": "rays/s",
-                               "ms_per_iteration": ms, "views": V, "views_per_rank": len(mine), "allreduce_bytes": int(table.numel() * 4),
-                               "active_fraction": float(active_idx.numel()) / float(T),
-                               "algorithmic_bytes_per_pixel": 456, "achieved_GBps_per_gpu": len(mine) * Hh * Ww * 456 / (ms / 1e3) / 1e9,
+                               "ms_per_iteration": ms, "views": V, "pixels_per_rank": n_px, "views_per_rank": n_px / HW,
+                               "exchange": "one kernel per GPU over NVLink peer memory: P2P reduce of the owned rows + sign step + P2P broadcast (csrc/peer.cu)",
+                               "sign_step_in_timed_region": True,
+                               "nvlink_bytes_read_per_gpu": nvlink_bytes, "nvlink_bytes_written_per_gpu": nvlink_bytes,
+                               "ms_gather_scatter_only": ms_local, "ms_exchange_and_update": ms - ms_local,
+                               "ms_per_iteration_nccl_allreduce_then_update": ms_nccl, "nccl_allreduce_bytes": T * 16,
+                               "active_fraction": active_fraction,
+                               "algorithmic_bytes_per_pixel": 456, "achieved_GBps_per_gpu": n_px * 456 / (ms / 1e3) / 1e9,
                                "scaling": "strong"}
-    del batches, table
+    del batches, part
+    ex.close()
+    del table, grad, init, ex
 
     # ---- config 5: retraining step ----
     N_rand = 4096
@@ -292,11 +357,15 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
         # the same step (render -> loss -> backward -> all-reduce -> fused Adam -> lr decay -> re-pack) as ONE CUDA graph
         from nerfail_b200 import train as ntrain
 
-        def time_graphed(bt, n_iter):
+        def time_graphed(bt, n_iter, peer=False):
             opt_g = nb.Adam(params_c + params_f, lr=5e-4, betas=(0.9, 0.999))
+            # peer: gradient average + Adam (sharded state) + parameter broadcast as ONE kernel per GPU over NVLink peer
+            # memory (dist.PeerAdam, csrc/peer.cu) instead of two NCCL all-reduces and a replicated full-size Adam
+            pex = nd.PeerAdam([net_c_, net_f_], opt_g, dev) if peer else None
             br = torch.stack([bt["rays"][:, 0:3], bt["rays"][:, 3:6]], 0).contiguous()
             kwg = dict(kw, perturb=1.0)
-            stepper = ntrain.GraphedTrainStep(br.shape[1], H, W, K, 32768, kwg, opt_g, 5e-4, 250, near=2.0, far=6.0, device=dev)
+            stepper = ntrain.GraphedTrainStep(br.shape[1], H, W, K, 32768, kwg, opt_g, 5e-4, 250, near=2.0, far=6.0, device=dev,
+                                              exchange=pex)
             for i in range(5):                                            # 3 eager warm-up steps, capture, one replay
                 stepper(br, bt["target"], i)
             torch.cuda.synchronize()
@@ -308,9 +377,17 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
                 stepper(br, bt["target"], 5 + i)
             e1.record()
             torch.cuda.synchronize()
-            return sync_max(e0.elapsed_time(e1)) / n_iter
+            t = sync_max(e0.elapsed_time(e1)) / n_iter
+            if pex is not None:
+                pex.ex.status()
+                del stepper
+                pex.close()
+            return t
+        net_c_, net_f_ = kw["network_fn"], kw["network_fine"]
         ms_graph = time_graphed(batch, 20)
         ms_graph_weak = time_graphed(batch_weak, 20)
+        ms_graph_peer = time_graphed(batch, 20, peer=True)
+        ms_graph_peer_weak = time_graphed(batch_weak, 20, peer=True)
         with torch.no_grad():                                            # restore the weights the other measurements use
             for p_, w_ in zip(params_c + params_f, sd0):
                 p_.copy_(w_)
@@ -325,7 +402,11 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
                               "dtype": "bf16", "optimizer_step": False, "allreduce_bytes": ar_bytes, "scaling": "strong",
                               "with_fused_adam_and_weight_repack": {"ms_per_step": ms16_adam, "value": N_rand / (ms16_adam / 1e3), "unit": "rays/s"},
                               "cuda_graph_step_with_adam": {"ms_per_step": ms_graph, "value": N_rand / (ms_graph / 1e3), "unit": "rays/s",
-                                                            "note": "whole optimisation step captured once (train.GraphedTrainStep), 20 replays"},
+                                                            "note": "whole optimisation step captured once (train.GraphedTrainStep), 20 replays; NCCL all-reduce + replicated Adam"},
+                              "cuda_graph_step_peer_adam": {"ms_per_step": ms_graph_peer, "value": N_rand / (ms_graph_peer / 1e3), "unit": "rays/s",
+                                                            "note": "same graph with dist.PeerAdam: average + sharded Adam + broadcast in one kernel per GPU over NVLink peer memory"},
+                              "cuda_graph_step_peer_adam_weak": {"ms_per_step": ms_graph_peer_weak, "rays_per_rank": N_rand, "global_batch": N_rand * world,
+                                                                 "value": N_rand * world / (ms_graph_peer_weak / 1e3), "unit": "rays/s"},
                               "cuda_graph_step_with_adam_weak": {"ms_per_step": ms_graph_weak, "rays_per_rank": N_rand, "global_batch": N_rand * world,
                                                                  "value": N_rand * world / (ms_graph_weak / 1e3), "unit": "rays/s"},
                               "weak_scaling_with_adam": {"ms_per_step": ms16_adam_weak, "rays_per_rank": N_rand, "global_batch": N_rand * world,
@@ -335,15 +416,37 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
     for p_ in params_c + params_f:
         p_.grad = None
 
-    # ---- 8-NN precompute of one view (create_index_and_dist.py:110-151) on rendered geometry ----
+    # ---- 8-NN precompute (create_index_and_dist.py:110-163) on rendered geometry: one view, and the sweep sharded by view ----
+    from nerfail_b200 import pipeline
+    poses = synth.camera_ring(8)
+    kwr = {k: v for k, v in kw.items()}
+    kwr.update(near=2.0, far=6.0)
+    base = torch.stack([pipeline.render_points(H, W, K, torch.tensor(poses[i][:3, :4]), 1024, **kwr) for i in (0, 3, 5)], 0)
+    qpts = pipeline.render_points(H, W, K, torch.tensor(poses[1 + rank % 2][:3, :4]), 1024, **kwr)
+    cand = base.reshape(-1, 3).contiguous()
+    # every rank answers 8 views of the sweep (weak scaling: view i -> rank i mod G, candidates replicated, no collective),
+    # index_and_dist + index_and_weight per view as the reference stores them; the views are this rank's rendered points
+    # shifted by a few 1e-4 so that no two queries are identical
+    sps = pipeline.SpatialPointSet(base)
+    n_knn = 8
+    my_views = {i: qpts + 1e-4 * (i + 1) for i in range(rank, n_knn * world, world)}
+    view_list = [my_views.get(i) for i in range(n_knn * world)]
+    pipeline.knn_sweep(view_list[:world], sps, rank=rank, world_size=world, keep=False)      # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    pipeline.knn_sweep(view_list, sps, rank=rank, world_size=world, keep=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_knn = sync_max(e0.elapsed_time(e1))
+    out["knn_sweep"] = {"metric": "8-NN precompute sweep, views/s (800x800 query views against P=3 base views, exact grid search + Gaussian weights)",
+                        "value": n_knn * world / (ms_knn / 1e3), "unit": "views/s", "views": n_knn * world, "ms_per_view_per_rank": ms_knn / n_knn,
+                        "query_pixels_per_s": n_knn * world * H * W / (ms_knn / 1e3), "scaling": "weak",
+                        "sharding": "view i -> rank i mod G, candidates replicated (23 MB), no collective"}
+    del my_views, view_list, sps
     if world == 1:
-        from nerfail_b200 import pipeline
-        poses = synth.camera_ring(8)
-        kwr = {k: v for k, v in kw.items()}
-        kwr.update(near=2.0, far=6.0)
-        base = torch.stack([pipeline.render_points(H, W, K, torch.tensor(poses[i][:3, :4]), 1024, **kwr) for i in (0, 3, 5)], 0)
-        qpts = pipeline.render_points(H, W, K, torch.tensor(poses[1][:3, :4]), 1024, **kwr)
-        cand = base.reshape(-1, 3).contiguous()
 
         def timed(fn, n):
             fn(); torch.cuda.synchronize()
@@ -520,6 +623,25 @@ def main():
         barrier()
         ms_e2e = max(e_start.elapsed_time(e_stop), 1e3 * (time.perf_counter() - t0))
 
+    # the same view with the reference's LITERAL chunking (625 passes of 1024 rays, NERFAIL_B200_STRICT_CHUNK=1): what
+    # chunk=1024 costs when it is not coalesced (results are bit-identical, tests/test_gpu_render.py)
+    ms_strict = None
+    if not args.no_extras:
+        import nerfail_b200.rendering  # noqa: F401
+        os.environ["NERFAIL_B200_STRICT_CHUNK"] = "1"
+        try:
+            with torch.no_grad():
+                nb.render(H, W, K, chunk=CHUNK, c2w=c2w_host, near=2.0, far=6.0, **kw)
+                barrier()
+                s0, s1 = ev(), ev()
+                s0.record()
+                nb.render(H, W, K, chunk=CHUNK, c2w=c2w_host, near=2.0, far=6.0, **kw)
+                s1.record()
+                barrier()
+                ms_strict = s0.elapsed_time(s1)
+        finally:
+            os.environ.pop("NERFAIL_B200_STRICT_CHUNK", None)
+
     extra = {}
     if not args.no_extras:
         extra = run_extras(args, dev, rank, world, dist, nb, ops, synth, kw)
@@ -540,6 +662,16 @@ def main():
     if rank == 0:
         peak_tf, _, how = measured_peaks()
         achieved_tf = mlp_flop / (mlp_ms / 1e3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture of this kernel
+        # (profiles/r02_mlp_traffic.json, written by scripts/ncu_traffic.py from the raw CSV export next to it), per sample,
+        # scaled to this run's average launch; null when no capture is committed
+        traffic, traffic_unit = None, "no committed ncu capture (profiles/r02_mlp_traffic.json missing)"
+        tpath = os.path.join(REPO, "profiles", "r02_mlp_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic = tj["dram_bytes_per_sample"] * (mlp_flop / FLOP_PER_SAMPLE) / max(1, n_mlp_launches)
+            traffic_unit = (f"bytes per launch = {tj['dram_bytes_per_sample']:.2f} B/sample (dram__bytes_read.sum + dram__bytes_write.sum of "
+                            f"{tj['source']}) x samples per launch; algorithmic 20 B/sample")
         line = {
             "metric": "render rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -559,21 +691,30 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"kernel": "nfb::mlp_fused_fwd_kernel", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01_v3_cta_group2.md (199.5 MB for 12.58 M
-                         # samples = 15.86 B/sample; algorithmic 20 B/sample) scaled to this run's average launch
-                         "traffic": 15.68 * (mlp_flop / FLOP_PER_SAMPLE) / max(1, n_mlp_launches),
-                         "traffic_unit": "bytes per launch = 15.68 B/sample (dram read + write of one ncu --set full capture, profiles/r01_final.md) x samples per launch",
+                         "traffic": traffic, "traffic_unit": traffic_unit,
                          "peak_source": f"{how} bf16_tflops_sustained", "launches": n_mlp_launches,
                          "avg_launch_ms": mlp_ms / max(1, n_mlp_launches),
                          "algorithmic_flop_per_sample": FLOP_PER_SAMPLE, "share_of_step": mlp_ms / ms},
         }
         if extra:
+            # the two workloads with a real exchange, strong scaling (fixed total work), at the top level so that the record
+            # of every N carries them: attack iteration of 100 views, retraining step of 4096 rays (one CUDA graph, PeerAdam)
+            line["strong"] = {"attack_ms": extra["attack_iteration"]["ms_per_iteration"],
+                              "train_ms": extra["retraining_step"]["cuda_graph_step_peer_adam"]["ms_per_step"],
+                              "attack_ms_nccl": extra["attack_iteration"]["ms_per_iteration_nccl_allreduce_then_update"],
+                              "train_ms_nccl": extra["retraining_step"]["cuda_graph_step_with_adam"]["ms_per_step"],
+                              "knn_views_per_s": extra["knn_sweep"]["value"]}
+            if ms_strict is not None:
+                extra["render_strict_chunk_1024"] = {"metric": "render rays/s with literal 1024-ray chunks (625 passes per view, NERFAIL_B200_STRICT_CHUNK=1)",
+                                                     "value": n_rays / (ms_strict / 1e3), "unit": "rays/s", "ms_per_view": ms_strict,
+                                                     "note": "host-bound: ~8 kernel launches per 1024-ray pass through Python"}
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = 32768                                         # ~14 s of CPU work on a 16-core host
-            v, dt, cores = cpu_reference_rays_per_s(n_cpu)
-            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n_cpu} random rays of the same view, coarse+fine, chunk 1024, {dt:.1f} s of torch-CPU fp32 (oracle/nerf_oracle.py)"}
+            v, dt, cores, kind = cpu_reference_rays_per_s(n_cpu)
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": kind,
+                                    "sample": f"{n_cpu} random rays of the same view, coarse+fine, chunk 1024, {dt:.1f} s of torch-CPU fp32 "
+                                              + ("(unmodified reference run_nerf.render(), oracle/_ref)" if kind == "reference" else "(oracle/nerf_oracle.py)")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -190,38 +190,54 @@ class PeerExchange:
             raise RuntimeError("PeerExchange spans the GPUs of one node (at most 8 ranks)")
         pad4 = lambda n: (int(n) + 3) // 4 * 4
         self.n_grad, self.n_value = pad4(n_grad), pad4(n_value)
-        sizes = (self.n_grad * 4, self.n_value * 4, int(lib.nfb_peer_flag_bytes()))
-        self._local, handles = [], []
+        # ONE allocation per rank, a multiple of 2 MiB (an IPC handle exports the whole underlying allocation, and small
+        # cudaMalloc blocks share one): [flag words | gradient | value], each part 256-byte aligned
+        al = lambda n: (n + 255) // 256 * 256
+        off_grad = al(int(lib.nfb_peer_flag_bytes()))
+        off_value = off_grad + al(self.n_grad * 4)
+        total = (off_value + al(self.n_value * 4) + (1 << 21) - 1) >> 21 << 21
+        self._opened = []
         with torch.cuda.device(self.device):
-            for nbytes in sizes:
-                p = C.c_void_p()
-                _lib.check(lib.nfb_peer_alloc(nbytes, C.byref(p)), "nfb_peer_alloc")
-                self._local.append(p.value)
-                h = C.create_string_buffer(64)
-                _lib.check(lib.nfb_peer_export(p, h), "nfb_peer_export")
-                handles.append(h.raw)
+            p = C.c_void_p()
+            _lib.check(lib.nfb_peer_alloc(total, C.byref(p)), "nfb_peer_alloc")
+            self._local = p.value
+            hbuf = C.create_string_buffer(64)
+            _lib.check(lib.nfb_peer_export(p, hbuf), "nfb_peer_export")
             everyone = [None] * self.world
             if self.world > 1:
-                dist.all_gather_object(everyone, (self.rank, handles), group=group)
+                dist.all_gather_object(everyone, (self.rank, hbuf.raw), group=group)
             else:
-                everyone = [(0, handles)]
-            self._opened = []
-            table = [[None] * self.world for _ in range(3)]
-            for r, hs in everyone:
-                for k in range(3):
-                    if r == self.rank:
-                        table[k][r] = self._local[k]
-                    else:
-                        q = C.c_void_p()
-                        _lib.check(lib.nfb_peer_import(C.create_string_buffer(hs[k], 64), C.byref(q)), "nfb_peer_import")
-                        self._opened.append(q.value)
-                        table[k][r] = q.value
-            arrs = [(C.c_void_p * self.world)(*table[k]) for k in range(3)]
+                everyone = [(0, hbuf.raw)]
+            bases = [None] * self.world
+            for r, hraw in everyone:
+                if r == self.rank:
+                    bases[r] = self._local
+                else:
+                    q = C.c_void_p()
+                    _lib.check(lib.nfb_peer_import(C.create_string_buffer(hraw, 64), C.byref(q)), "nfb_peer_import")
+                    self._opened.append(q.value)
+                    bases[r] = q.value
+            arrs = [(C.c_void_p * self.world)(*[b + o for b in bases]) for o in (off_grad, off_value, 0)]
             h = C.c_void_p()
             _lib.check(lib.nfb_peer_create(C.byref(h), self.rank, self.world, arrs[0], arrs[1], arrs[2]), "nfb_peer_create")
             self._h = h
-            self.grad = torch.as_tensor(_DeviceMemory(self._local[0], self.n_grad), device=self.device)
-            self.value = torch.as_tensor(_DeviceMemory(self._local[1], self.n_value), device=self.device)
+            self.grad = torch.as_tensor(_DeviceMemory(self._local + off_grad, self.n_grad), device=self.device)
+            self.value = torch.as_tensor(_DeviceMemory(self._local + off_value, self.n_value), device=self.device)
+            if self.world > 1:
+                # sanity check of the mapping before any kernel trusts it: every rank marks its own buffer, reads the
+                # peers' marks through the opened pointers, and clears its mark again
+                self.value[:4] = float(1000 + self.rank)
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=group)
+                for r in range(self.world):
+                    if r != self.rank:
+                        seen = torch.as_tensor(_DeviceMemory(bases[r] + off_value, 4), device=self.device).cpu()
+                        if not bool((seen == float(1000 + r)).all()):
+                            raise RuntimeError(f"PeerExchange: rank {self.rank} does not see rank {r}'s buffer through its IPC mapping "
+                                               f"(read {seen.tolist()})")
+                dist.barrier(group=group)
+                self.value[:4] = 0.0
+                torch.cuda.synchronize(self.device)
         if self.world > 1:
             dist.barrier(group=group)           # every rank has opened every buffer before anyone launches
 
@@ -259,9 +275,11 @@ class PeerExchange:
             for p in self._opened:
                 lib.nfb_peer_close(p)
             self.grad = self.value = None
-            for p in self._local:
-                lib.nfb_peer_free(p)
-            self._opened, self._local = [], []
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier()                  # ... and nobody frees memory a peer still has mapped
+            if self._local:
+                lib.nfb_peer_free(self._local)
+            self._opened, self._local = [], None
 
     def __del__(self):
         try:

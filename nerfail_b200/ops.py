@@ -577,17 +577,12 @@ def philox_uniform(seed: int, offset: int, stream_id: int, n: int, device=None) 
     return out
 
 
-_philox_state = {"seed": None, "offset": 0}
-
-
 def next_philox(device=None) -> tuple:
-    """(seed, offset) for one kernel-side draw: the seed is torch's (so torch.manual_seed makes renders reproducible), the
-    offset counts this process's draws since that seed was set."""
-    seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
-    if _philox_state["seed"] != seed:
-        _philox_state["seed"], _philox_state["offset"] = seed, 0
-    _philox_state["offset"] += 1
-    return seed, _philox_state["offset"]
+    """(seed, offset) for one kernel-side draw, taken from torch's default CPU generator (two 62-bit integers: no GPU
+    launch, no synchronisation), so torch.manual_seed makes a stochastic render reproducible exactly as it does for the
+    torch.rand draws this replaces, and consecutive calls get unrelated streams."""
+    k = torch.randint(0, 1 << 62, (2,), dtype=torch.int64)
+    return int(k[0]), int(k[1])
 
 
 def render_rays_fused(coarse: "FusedMLP", fine: Optional["FusedMLP"], rays: torch.Tensor, N_samples: int, N_importance: int,

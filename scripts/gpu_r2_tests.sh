@@ -13,5 +13,5 @@ done
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1
 echo "smoke exit $?" >> $O/summary.txt
 cat $O/summary.txt
-grep -hE "^(FAILED|ERROR)|passed|failed|config 5 bf16|seed [0-9]+:|mean difference|config 1 bf16" $O/test_*.log | tail -40
+grep -hE "^(FAILED|ERROR)|passed|failed|config 5 bf16|seed [0-9]+:|mean difference|config 1" $O/test_*.log | tail -40
 tail -n 2 $O/smoke.log
