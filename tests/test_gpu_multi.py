@@ -75,6 +75,7 @@ def _run_rank(rank, world, dev):
     assert torch.equal(got[:, 3], init[:, 3])
     assert float((got - want).abs().max()) <= 1e-6, float((got - want).abs().max())      # sign step: exact up to the fp32 sum order
     ex.close()
+    print(f"[rank {rank}] attack exchange ok", flush=True)
     # ---- retraining step exchange: mean gradient + Adam, optimiser state sharded ----
     n, p0, agrads, pwant = _adam_case(world)
     ex = nd.PeerExchange(n, n, dev)
@@ -97,10 +98,12 @@ def _run_rank(rank, world, dev):
     assert float((got - pwant).abs().max()) <= 2e-3 * moved, (float((got - pwant).abs().max()), moved)
     # every rank holds the same parameters bit for bit
     if world > 1:
-        both = [torch.empty_like(got) for _ in range(world)]
-        dist.all_gather(both, got.to(dev) if dist.get_backend() == "nccl" else got)
-        assert all(torch.equal(both[0].cpu(), b.cpu()) for b in both)
+        mine = got.to(dev)
+        both = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        assert all(torch.equal(both[0], b) for b in both)
     ex.close()
+    print(f"[rank {rank}] adam exchange ok", flush=True)
 
 
 def _run_training(rank, world, dev):
@@ -147,6 +150,7 @@ def _run_training(rank, world, dev):
             state = ex.state_for_checkpoint()
             assert len(state["state"]) == 48
             ex.close()
+        print(f"[rank {rank}] training mode {mode} ok", flush=True)
         return sd, losses
 
     sd_a, l_a = run("nccl")
@@ -171,24 +175,35 @@ def test_exchange_kernels_single_rank(cuda):
     _run_training(0, 1, cuda)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, what):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if what == "kernels":                                 # parity test, not a timing: a fault is reported at the launch that caused it
+        os.environ["CUDA_LAUNCH_BLOCKING"] = "1"          # (not for the training section: it captures a CUDA graph)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        _run_rank(rank, world, dev)
-        _run_training(rank, world, dev)
+        (_run_rank if what == "kernels" else _run_training)(rank, world, dev)
+        torch.cuda.synchronize(dev)
         out[rank] = True
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_exchange_kernels_over_peer_memory(world):
+def _spawn(world, what):
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     port = _free_port()
     out = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, what), nprocs=world, join=True)
     assert all(out.get(r) for r in range(world))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_exchange_kernels_over_peer_memory(world):
+    _spawn(world, "kernels")
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_peer_adam_training_over_peer_memory(world):
+    _spawn(world, "training")
