@@ -59,6 +59,18 @@ NFB_API int         nfb_device_cc(void);
 NFB_API int nfb_get_rays(int H, int W, const double* K_host, const float* c2w_host,
                  float near_, float far_, float* rays, void* stream);
 
+/* The ray batch of render(rays=(rays_o, rays_d)) for use_viewdirs = True, ndc = False (the training step's call).
+ * replaces: run_nerf.py:95-123 (viewdirs = rays_d / norm, near / far columns, two concatenations) in one launch.
+ * rays_o, rays_d [N,3] -> rays [N,11].                                                                   */
+NFB_API int nfb_rays_from_batch(const float* rays_o, const float* rays_d, int64_t N, float near_, float far_, float* rays,
+                                void* stream);
+
+/* The training loss with its gradient in one pass.
+ * replaces: img2mse(rgb, target) + img2mse(rgb0, target) (run_nerf.py:781-789, run_nerf_helpers.py:9) and their autograd.
+ * rgb, rgb0 (or NULL), target: n floats; out3 = (loss, mse(rgb), mse(rgb0)); g_rgb / g_rgb0 = 2 (x - target) / n.  */
+NFB_API int nfb_mse_loss2(const float* rgb, const float* rgb0, const float* target, int64_t n, float* out3, float* g_rgb,
+                          float* g_rgb0, void* stream);
+
 /* Coarse depths. replaces: run_nerf.py:357-379 (linspace / lindisp / stratified jitter)
  * rays [R,11]; t_rand [R,S] uniform numbers or NULL (perturb == 0); z_vals out [R,S].               */
 NFB_API int nfb_coarse_z(const float* rays, int R, int S, int lindisp, const float* t_rand,

@@ -25,6 +25,8 @@ SIGNATURES = {
     "nfb_launch_count": (C.c_uint64, []),
     "nfb_device_cc": (c_int, []),
     "nfb_get_rays": (c_int, [c_int, c_int, c_ptr, c_ptr, C.c_float, C.c_float, c_ptr, c_ptr]),
+    "nfb_rays_from_batch": (c_int, [c_ptr, c_ptr, c_i64, C.c_float, C.c_float, c_ptr, c_ptr]),
+    "nfb_mse_loss2": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nfb_coarse_z": (c_int, [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "nfb_philox_uniform": (c_int, [C.c_uint64, C.c_uint64, C.c_uint32, c_i64, c_ptr, c_ptr]),
     "nfb_coarse_z_rng": (c_int, [c_ptr, c_int, c_int, c_int, C.c_uint64, C.c_uint64, c_ptr, c_ptr]),

@@ -68,6 +68,55 @@ __global__ void get_rays_kernel(int H, int W, float fx, float fy, float cx, floa
   }
 }
 
+// render(rays=(rays_o, rays_d)) of run_nerf.py:95-123 for use_viewdirs = True, ndc = False: the [N,11] ray batch
+// (o, d, near, far, d / |d|) from a [2,N,3] batch in one launch (the reference: norm, div, two ones_like, two cats).
+__global__ void rays_from_batch_kernel(const float* __restrict__ o, const float* __restrict__ d, int64_t n, float near_,
+                                       float far_, float* __restrict__ rays) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const float d0 = __ldg(d + 3 * p), d1 = __ldg(d + 3 * p + 1), d2 = __ldg(d + 3 * p + 2);
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+    float* r = rays + p * 11;
+    r[0] = __ldg(o + 3 * p); r[1] = __ldg(o + 3 * p + 1); r[2] = __ldg(o + 3 * p + 2);
+    r[3] = d0; r[4] = d1; r[5] = d2;
+    r[6] = near_; r[7] = far_;
+    r[8] = __fdiv_rn(d0, nrm); r[9] = __fdiv_rn(d1, nrm); r[10] = __fdiv_rn(d2, nrm);
+  }
+}
+
+// loss = img2mse(rgb, target) + img2mse(rgb0, target) (run_nerf.py:781-789, run_nerf_helpers.py:9) with its gradient in the
+// same pass: out[0] = loss, out[1] = mse(rgb), out[2] = mse(rgb0); g = 2 (rgb - target) / n, g0 likewise.  One CTA, fixed
+// reduction order (deterministic); n = 3 R is a few thousand to a few hundred thousand elements.
+__global__ void __launch_bounds__(1024)
+mse_loss2_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0, const float* __restrict__ target, int64_t n,
+                 float* __restrict__ out, float* __restrict__ g, float* __restrict__ g0) {
+  __shared__ float s0[32], s1[32];
+  float a = 0.f, b = 0.f;
+  const float scale = 2.f / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float t = __ldg(target + i);
+    const float e = rgb[i] - t;
+    a = fmaf(e, e, a);
+    g[i] = scale * e;
+    if (rgb0) {
+      const float e0 = rgb0[i] - t;
+      b = fmaf(e0, e0, b);
+      g0[i] = scale * e0;
+    }
+  }
+  a = warp_sum(a); b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = a; s1[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = threadIdx.x < (blockDim.x >> 5) ? s0[threadIdx.x] : 0.f;
+    b = threadIdx.x < (blockDim.x >> 5) ? s1[threadIdx.x] : 0.f;
+    a = warp_sum(a); b = warp_sum(b);
+    if (threadIdx.x == 0) {
+      const float m = a / (float)n, m0 = b / (float)n;
+      out[0] = m + m0; out[1] = m; out[2] = m0;
+    }
+  }
+}
+
 __device__ __forceinline__ float coarse_depth(float near_, float far_, int i, int S, int lindisp) {
   const float t = linspace01(i, S);
   const float omt = __fsub_rn(1.f, t);
@@ -350,6 +399,20 @@ static int coarse_z_launch(const float* rays, int R, int S, int lindisp, const f
 
 int nfb_coarse_z(const float* rays, int R, int S, int lindisp, const float* t_rand, float* z_vals, void* stream) {
   return coarse_z_launch(rays, R, S, lindisp, t_rand, nfb::Rng{0ull, 0ull, 0}, z_vals, stream);
+}
+
+int nfb_rays_from_batch(const float* rays_o, const float* rays_d, int64_t N, float near_, float far_, float* rays, void* stream) {
+  NFB_REQUIRE(rays_o && rays_d && rays && N >= 0, "rays_from_batch: bad argument");
+  if (N == 0) return NFB_OK;
+  nfb::rays_from_batch_kernel<<<nfb::grid_for(N, 256, 8), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, N, near_, far_, rays);
+  return nfb::check_launch("rays_from_batch");
+}
+
+int nfb_mse_loss2(const float* rgb, const float* rgb0, const float* target, int64_t n, float* out3, float* g_rgb, float* g_rgb0,
+                  void* stream) {
+  NFB_REQUIRE(rgb && target && out3 && g_rgb && n > 0 && (!rgb0 || g_rgb0), "mse_loss2: bad argument");
+  nfb::mse_loss2_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rgb, rgb0, target, n, out3, g_rgb, g_rgb0);
+  return nfb::check_launch("mse_loss2");
 }
 
 int nfb_philox_uniform(uint64_t seed, uint64_t offset, uint32_t stream_id, int64_t n, float* out, void* stream) {

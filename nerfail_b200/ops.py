@@ -48,6 +48,43 @@ def get_ray_batch(H: int, W: int, K, c2w, near: float, far: float, device=None) 
     return rays
 
 
+def rays_from_batch(rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float) -> torch.Tensor:
+    """[N,11] ray batch (o, d, near, far, d / |d|) of render(rays=...) — run_nerf.py:95-123 for use_viewdirs, ndc=False."""
+    _require_cuda(rays_o, rays_d)
+    o, d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    rays = torch.empty((o.shape[0], 11), dtype=torch.float32, device=o.device)
+    with torch.cuda.device(o.device):
+        check(_lib.load().nfb_rays_from_batch(ptr(o), ptr(d), o.shape[0], float(near), float(far), ptr(rays), stream()),
+              "nfb_rays_from_batch")
+    return rays
+
+
+class MseLoss2Fn(torch.autograd.Function):
+    """loss = img2mse(rgb, target) + img2mse(rgb0, target) (run_nerf.py:781-789) with the gradient produced in the forward
+    pass: one kernel instead of ~12 element-wise / reduction launches forward and ~8 backward.  Returns (loss, mse [2])."""
+
+    @staticmethod
+    def forward(ctx, rgb, rgb0, target):
+        rgb, target = _f32(rgb), _f32(target)
+        rgb0 = _f32(rgb0) if rgb0 is not None else None
+        out = torch.empty(3, dtype=torch.float32, device=rgb.device)
+        g = torch.empty_like(rgb)
+        g0 = torch.empty_like(rgb0) if rgb0 is not None else None
+        with torch.cuda.device(rgb.device):
+            check(_lib.load().nfb_mse_loss2(ptr(rgb), ptr(rgb0), ptr(target), rgb.numel(), ptr(out), ptr(g), ptr(g0), stream()),
+                  "nfb_mse_loss2")
+        ctx.save_for_backward(g, g0 if g0 is not None else torch.empty(0, device=rgb.device))
+        ctx.has0 = g0 is not None
+        mse = out[1:3]
+        ctx.mark_non_differentiable(mse)
+        return out[0], mse
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_mse):
+        g, g0 = ctx.saved_tensors
+        return g_loss * g, (g_loss * g0 if ctx.has0 else None), None
+
+
 def coarse_z(rays: torch.Tensor, n_samples: int, lindisp: bool = False, t_rand: Optional[torch.Tensor] = None,
              rng: Optional[tuple] = None):
     """z_vals [R, n_samples] (run_nerf.py:357-379).  rng = (seed, offset): stratified jitter drawn in the kernel (Philox)."""

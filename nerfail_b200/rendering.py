@@ -246,6 +246,11 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far
         dev = c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda else torch.device("cuda")
         rays_b = ops.get_ray_batch(H, W, K, c2w, near, far, device=dev)
         sh = (H, W, 3)
+    elif (c2w is None and not ndc and c2w_staticcam is None and use_viewdirs and isinstance(rays, torch.Tensor) and rays.is_cuda
+          and rays.dim() == 3 and rays.shape[0] == 2 and rays.shape[-1] == 3 and not rays.requires_grad):
+        # the training step's call (run_nerf.py:776: rays=batch_rays [2,N,3]): one kernel builds the [N,11] batch
+        rays_b = ops.rays_from_batch(rays[0], rays[1], near, far)
+        sh = (rays.shape[1], 3)
     else:
         if c2w is not None:
             rays_o, rays_d = nerf.get_rays(H, W, K, c2w)

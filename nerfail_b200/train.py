@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import dist as nd
-from . import nerf
+from . import nerf, ops
 from .optim import decayed_lrate, set_lrate
 from .rendering import render
 
@@ -98,13 +98,12 @@ def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwarg
     with torch.enable_grad():
         rgb, disp, acc, extras = render(H, W, K, chunk=chunk, rays=batch_rays, retraw=True, **kw)
         optimizer.zero_grad()
-        img_loss = nerf.img2mse(rgb, target_s)
-        loss = img_loss
-        out = {"psnr": _psnr(img_loss.detach())}
+        # img2mse(fine) + img2mse(coarse) and their gradients in one kernel (run_nerf.py:781-789)
+        loss, mse = ops.MseLoss2Fn.apply(rgb, extras.get("rgb0"), target_s[..., :3])
+        psnr = _psnr(mse)
+        out = {"psnr": psnr[0]}
         if "rgb0" in extras:
-            img_loss0 = nerf.img2mse(extras["rgb0"], target_s)
-            loss = loss + img_loss0
-            out["psnr0"] = _psnr(img_loss0.detach())
+            out["psnr0"] = psnr[1]
         loss.backward()
     _, world_size = nd.world()
     if exchange is not None:

@@ -424,3 +424,32 @@ def test_fused_adam_matches_torch_adam_and_shares_its_state_dict(cuda):
     before = got_p[0].detach().clone()
     got_o.step()
     assert torch.equal(got_p[0].detach(), before)
+
+
+def test_rays_from_batch_and_fused_mse_loss(cuda):
+    """The two small fusions of the training step: the [N,11] ray batch of render(rays=batch_rays) (run_nerf.py:95-123) bit
+    for bit against the oracle's torch restatement, and img2mse(fine) + img2mse(coarse) with its gradient (run_nerf.py:781-791)
+    against torch autograd."""
+    from nerfail_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    for n in (1, 513, 4096):
+        o, d = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g) * 3
+        want = no.rays_from_batch(torch.stack([o, d], 0), 2.0, 6.0)
+        got = ops.rays_from_batch(o.to(cuda), d.to(cuda), 2.0, 6.0).cpu()
+        assert torch.equal(got[:, :8], want[:, :8])
+        assert float((got[:, 8:] - want[:, 8:]).abs().max()) <= 1.2e-7          # d / |d|: torch.norm may round the sum differently by 1 ulp
+        rgb, rgb0, tgt = torch.rand(n, 3, generator=g), torch.rand(n, 3, generator=g), torch.rand(n, 3, generator=g)
+        a, a0 = rgb.clone().requires_grad_(True), rgb0.clone().requires_grad_(True)
+        ref = torch.mean((a - tgt) ** 2) + torch.mean((a0 - tgt) ** 2)
+        ref.backward()
+        b, b0 = rgb.to(cuda).requires_grad_(True), rgb0.to(cuda).requires_grad_(True)
+        loss, mse = ops.MseLoss2Fn.apply(b, b0, tgt.to(cuda))
+        (loss * 1.0).backward()
+        assert abs(float(loss) - float(ref)) <= 2e-6 * float(ref) + 1e-9
+        assert abs(float(mse[0]) - float(torch.mean((rgb - tgt) ** 2))) <= 2e-6 and abs(float(mse[1]) - float(torch.mean((rgb0 - tgt) ** 2))) <= 2e-6
+        assert float((b.grad.cpu() - a.grad).abs().max()) <= 1e-6 * float(a.grad.abs().max()) + 1e-12
+        assert float((b0.grad.cpu() - a0.grad).abs().max()) <= 1e-6 * float(a0.grad.abs().max()) + 1e-12
+        c = rgb.to(cuda).requires_grad_(True)                                    # no coarse image (N_importance = 0)
+        l1, m1 = ops.MseLoss2Fn.apply(c, None, tgt.to(cuda))
+        l1.backward()
+        assert abs(float(l1) - float(torch.mean((rgb - tgt) ** 2))) <= 2e-6 and float(m1[1]) == 0.0
