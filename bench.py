@@ -207,50 +207,54 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
     init = table.clone()
     grad = ex.grad[:T * 4].view(P, Hh, Ww, 4)
     active_fraction = float((table0[..., 3] > 0).float().mean())
-    VB = 10                                     # views per kernel launch (the reference attack batches 8, attack_NeRFail_S.py:81)
+    # This rank's pixels of the 100-view batch as ONE contiguous [1,2,n_px,8] weight / index tensor (the GaussNet kernels are
+    # per pixel: a shard is a pixel range, dist.shard_pixels), every view with its own random neighbours, generated ten
+    # views at a time.  One gather launch and one scatter launch per iteration cover the whole shard.
     gd = torch.Generator(device=dev).manual_seed(100 + rank)
-    base_idx = torch.arange(HW, device=dev).reshape(1, Hh, Ww, 1)
-    batches = []
-    for _ in range(2):                          # two distinct 10-view batches, cycled (820 MB of weights/indices)
-        idx = (base_idx + torch.randint(0, P, (VB, 1, 1, 1), device=dev, generator=gd) * HW
-               + torch.randint(-400, 401, (VB, Hh, Ww, 8), device=dev, generator=gd)).clamp_(0, T - 1).float()
-        dist_ = torch.sort(torch.randn(VB, Hh, Ww, 8, device=dev, generator=gd).abs() * 0.01, dim=-1).values
-        w_idx = ops.gauss_weights(torch.stack([dist_, idx], 1), 0.02)
-        ori = torch.randint(0, 256, (VB, Hh, Ww, 4), device=dev, generator=gd, dtype=torch.uint8)
-        gx = torch.randn(VB, Hh, Ww, 4, device=dev, generator=gd)
-        batches.append((w_idx, ori, gx))
-        del idx, dist_
-    full_views, rem_px = n_px // HW, n_px % HW
-    part = None
-    if rem_px:                                  # this rank's part of a view: rem_px / W rows as their own contiguous tensors
-        rr = rem_px // Ww
-        w0, o0, g0 = batches[0]
-        part = (w0[:1, :, :rr].contiguous(), o0[:1, :rr].contiguous(), g0[:1, :rr].contiguous())
+    rows = n_px // Ww
+    w_idx = torch.empty((1, 2, rows, Ww, 8), dtype=torch.float32, device=dev)
+    ori = torch.empty((1, rows, Ww, 4), dtype=torch.uint8, device=dev)
+    gx = torch.empty((1, rows, Ww, 4), dtype=torch.float32, device=dev)
+    r0 = 0
+    while r0 < rows:
+        nr = min(10 * Hh, rows - r0)
+        pix = (torch.arange(r0 * Ww, (r0 + nr) * Ww, device=dev) % HW).reshape(1, nr, Ww, 1)      # pixel index inside its view
+        view_of_row = torch.randint(0, P, ((nr + Hh - 1) // Hh + 1, 1, 1), device=dev, generator=gd).repeat_interleave(Hh, 0)[:nr]
+        idx = (pix + view_of_row.reshape(1, nr, 1, 1) * HW
+               + torch.randint(-400, 401, (1, nr, Ww, 8), device=dev, generator=gd)).clamp_(0, T - 1).float()
+        dist_ = torch.sort(torch.randn(1, nr, Ww, 8, device=dev, generator=gd).abs() * 0.01, dim=-1).values
+        w_idx[:, :, r0:r0 + nr] = ops.gauss_weights(torch.stack([dist_, idx], 1), 0.02)
+        ori[:, r0:r0 + nr] = torch.randint(0, 256, (1, nr, Ww, 4), device=dev, generator=gd, dtype=torch.uint8)
+        gx[:, r0:r0 + nr] = torch.randn(1, nr, Ww, 4, device=dev, generator=gd)
+        del idx, dist_, pix
+        r0 += nr
     tshape = (P, Hh, Ww, 4)
+    side = torch.cuda.Stream(device=dev)
+    grad_ready = torch.cuda.Event()
 
-    def scatter_views():
-        done, i = 0, 0
-        while done < full_views:
-            w_idx, ori, gx = batches[i % len(batches)]
-            nb_ = min(VB, full_views - done)
-            x, x_rgba = ops.gauss_gather_fwd(table.reshape(-1, 4), w_idx[:nb_], ori[:nb_], 32.0)
-            ops.gauss_scatter_bwd(None, gx[:nb_], x, w_idx[:nb_], ori[:nb_], 32.0, tshape, out=grad)
-            done += nb_; i += 1
-        if part is not None:
-            x, x_rgba = ops.gauss_gather_fwd(table.reshape(-1, 4), part[0], part[1], 32.0)
-            ops.gauss_scatter_bwd(None, part[2], x, part[0], part[1], 32.0, tshape, out=grad)
+    def scatter_views(overlap_zero=False):
+        main = torch.cuda.current_stream(dev)
+        if overlap_zero:            # the gradient is zeroed on a side stream beside the gather (which does not touch it)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                grad.zero_()
+                grad_ready.record(side)
+        else:
+            grad.zero_()
+        x, x_rgba = ops.gauss_gather_fwd(table.reshape(-1, 4), w_idx, ori, 32.0)
+        if overlap_zero:
+            main.wait_event(grad_ready)
+        ops.gauss_scatter_bwd(None, gx, x, w_idx, ori, 32.0, tshape, out=grad)
 
     def attack_iter():
         # attack_NeRFail_S.py:317-392 minus the classifier: zero the gradient, forward + backward of this rank's pixels,
         # then ONE kernel per GPU that sums the partial gradients over NVLink peer memory, takes the sign step on the rows it
         # owns and writes them into every rank's table (csrc/peer.cu) - the I-FGSM update is inside the timed iteration
-        grad.zero_()
-        scatter_views()
+        scatter_views(overlap_zero=True)
         ex.attack_step(init.reshape(-1, 4), T, 1.0, 8.0)
 
     def attack_iter_nccl():
         # the round-1 form for comparison: NCCL all-reduce of the whole gradient table, then the update as its own kernels
-        grad.zero_()
         scatter_views()
         nd.attack_sign_step_(table, grad, init, 1.0, 8.0)
 
@@ -271,7 +275,7 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
     ms = time_iters(attack_iter)
     ex.status()
     ms_nccl = time_iters(attack_iter_nccl)
-    ms_local = time_iters(lambda: (grad.zero_(), scatter_views()))
+    ms_local = time_iters(lambda: scatter_views(overlap_zero=True))
     px = V * HW
     slice_rows = (T + world - 1) // world
     nvlink_bytes = int(active_fraction * slice_rows * 16 * (world - 1))
@@ -285,7 +289,7 @@ def run_extras(args, dev, rank, world, dist, nb, ops, synth, kw):
                                "active_fraction": active_fraction,
                                "algorithmic_bytes_per_pixel": 456, "achieved_GBps_per_gpu": n_px * 456 / (ms / 1e3) / 1e9,
                                "scaling": "strong"}
-    del batches, part
+    del w_idx, ori, gx
     ex.close()
     del table, grad, init, ex
 

@@ -299,6 +299,14 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// two fp32 additions in one instruction (add.rn.f32x2 -> FADD2 on sm_100): the bias add of the accumulator drain
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long a, b, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(r));
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -713,10 +721,10 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
             float h[32];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              h[4 * j] = __uint_as_float(v[4 * j]) + b4[j].x;
-              h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4[j].y;
-              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4[j].z;
-              h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4[j].w;
+              h[4 * j] = __uint_as_float(v[4 * j]); h[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]); h[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+              add2(h[4 * j], h[4 * j + 1], b4[j].x, b4[j].y);
+              add2(h[4 * j + 2], h[4 * j + 3], b4[j].z, b4[j].w);
             }
             if (s == 7) {                              // alpha_linear on the fp32 activations (run_nerf_helpers.py:110)
 #pragma unroll

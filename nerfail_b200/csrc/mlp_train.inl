@@ -451,8 +451,10 @@ mlp_train_kernel(const TrainArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b = reinterpret_cast<const float4*>(bias_s + col0)[j];     // loaded at use: 32 fewer live registers
-              h[4 * j] = __uint_as_float(v[4 * j]) + b.x; h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z; h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+              h[4 * j] = __uint_as_float(v[4 * j]); h[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]); h[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+              add2(h[4 * j], h[4 * j + 1], b.x, b.y);
+              add2(h[4 * j + 2], h[4 * j + 3], b.z, b.w);
             }
             if (s == 7) {
 #pragma unroll
