@@ -999,11 +999,22 @@ int64_t nfb_mlp_param_count(const nfb_mlp_t* h) { return h ? h->n_params : nfb::
 int nfb_mlp_update(nfb_mlp_t* h, const float* params, int64_t n_params, void* stream) {
   NFB_REQUIRE(h && params, "mlp_update: null pointer");
   NFB_REQUIRE(n_params == h->n_params, "mlp_update: expected %lld parameters, got %lld", (long long)h->n_params, (long long)n_params);
-  nfb::pack_weights_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image, h->side);
-  int rc = nfb::check_launch("mlp_update");
-  if (rc) return rc;
-  nfb::tr::pack_weights_T_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image_t);
-  rc = nfb::check_launch("mlp_update.transposed");
+  // NERFAIL_B200_PACK=split: the two one-element-per-thread kernels (the readable specification of the layouts) instead of
+  // the fused 16-bytes-per-thread kernel; the images are bit-identical (tests/test_gpu_mlp.py)
+  const char* pack_env = getenv("NERFAIL_B200_PACK");
+  const bool split = pack_env && pack_env[0] == 's';
+  int rc;
+  if (split) {
+    nfb::pack_weights_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image, h->side);
+    rc = nfb::check_launch("mlp_update");
+    if (rc) return rc;
+    nfb::tr::pack_weights_T_kernel<<<nfb::sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(params, h->image_t);
+    rc = nfb::check_launch("mlp_update.transposed");
+  } else {
+    const int units = (nfb::TOTAL_BLOCKS + nfb::tr::TOTAL_BLOCKS_T) * nfb::TILE_M * 8;
+    nfb::tr::pack_both_kernel<<<(units + 255) / 256, 256, 0, (cudaStream_t)stream>>>(params, h->image, h->image_t, h->side);
+    rc = nfb::check_launch("mlp_update");
+  }
   if (rc) return rc;
   // stream-ordered device-to-device copy of the fp32 side parameters into this network's constant-memory entry (a network
   // that holds none right now copies them when it acquires one, ensure_cslot)

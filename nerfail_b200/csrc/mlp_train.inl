@@ -81,6 +81,85 @@ __global__ void pack_weights_T_kernel(const float* __restrict__ params, __nv_bfl
   }
 }
 
+// Both weight images and the fp32 side parameters of one network in ONE launch (nfb_mlp_update): a thread produces one
+// 16-byte unit (8 bf16) of an image.  Forward image: unit-fastest mapping (8 lanes read 64 consecutive floats of a weight
+// row); transposed image: row-fastest mapping (32 lanes read 32 consecutive input features of one output row), so both
+// read the fp32 parameters coalesced.  Same bits as pack_weights_kernel / pack_weights_T_kernel (kept as the readable
+// specification and used by the tests' cross-check); 4-5x faster, which matters once a step is a few hundred microseconds.
+__device__ __forceinline__ float fwd_image_value(const float* __restrict__ params, const ParamLayout& pl, int s, int chunk, int n, int kk) {
+  if (s <= 7) {
+    const int in = (s == 0) ? CH_PTS : (s == 5 ? W_ + CH_PTS : W_);
+    int col;
+    if (s == 0) col = (kk < CH_PTS) ? kk : -1;
+    else if (s == 5) col = (chunk == 4) ? ((kk < CH_PTS) ? kk : -1) : CH_PTS + chunk * KCH + kk;
+    else col = chunk * KCH + kk;
+    return col >= 0 ? __ldg(params + pl.w_pts[s] + (int64_t)n * in + col) : 0.f;
+  }
+  if (s == 8) return __ldg(params + pl.w_feat + (int64_t)n * W_ + chunk * KCH + kk);
+  const int col = chunk < 4 ? chunk * KCH + kk : ((kk < CH_DIR) ? W_ + kk : -1);
+  return col >= 0 ? __ldg(params + pl.w_views + (int64_t)n * (W_ + CH_DIR) + col) : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+pack_both_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ image, __nv_bfloat16* __restrict__ image_t,
+                 MlpSide* __restrict__ side) {
+  const ParamLayout pl = param_layout();
+  constexpr int UNITS_PER_BLOCK = TILE_M * 8;
+  const int total = (TOTAL_BLOCKS + TOTAL_BLOCKS_T) * UNITS_PER_BLOCK;
+  for (int uid = blockIdx.x * blockDim.x + threadIdx.x; uid < total; uid += gridDim.x * blockDim.x) {
+    int blk = uid / UNITS_PER_BLOCK;
+    const int within = uid % UNITS_PER_BLOCK;
+    float v[8];
+    char* dst;
+    int nrow, unit;
+    if (blk < TOTAL_BLOCKS) {
+      nrow = within >> 3; unit = within & 7;
+      int s = 0;
+#pragma unroll
+      for (int t = 1; t < NSTEP; ++t) s += (blk >= step_block0(t)) ? 1 : 0;
+      const int local = blk - step_block0(s);
+      const int halves = step_halves(s);
+      const int chunk = local / halves, half = local % halves;
+      const int n = half * 128 + nrow;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = fwd_image_value(params, pl, s, chunk, n, unit * 8 + q);
+      dst = reinterpret_cast<char*>(image) + (int64_t)blk * CHUNK_BYTES;
+    } else {
+      blk -= TOTAL_BLOCKS;
+      nrow = within & 127; unit = within >> 7;
+      int b, local;
+      if (blk < 4) { b = 0; local = blk; } else { b = 1 + (blk - 4) / 8; local = (blk - 4) % 8; }
+      const int chunk = local / 2, half = local % 2;
+      const int n = half * 128 + nrow;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = chunk * KCH + unit * 8 + q;
+        if (b == 0) v[q] = __ldg(params + pl.w_views + (int64_t)k * (W_ + CH_DIR) + n);
+        else if (b == 1) v[q] = __ldg(params + pl.w_feat + (int64_t)k * W_ + n);
+        else {
+          const int l = 9 - b;
+          const int in = (l == 5) ? W_ + CH_PTS : W_;
+          v[q] = __ldg(params + pl.w_pts[l] + (int64_t)k * in + n + (l == 5 ? CH_PTS : 0));
+        }
+      }
+      dst = reinterpret_cast<char*>(image_t) + (int64_t)blk * CHUNK_BYTES;
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + nrow * 128 + (((unit ^ (nrow & 7)) & 7) << 4)) = o;
+  }
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nt = gridDim.x * blockDim.x;
+  for (int i = t; i < 8 * W_; i += nt) side->bias[i / W_][i % W_] = params[pl.b_pts[i / W_] + i % W_];
+  for (int i = t; i < W_; i += nt) { side->bias_feat[i] = params[pl.b_feat + i]; side->w_alpha[i] = params[pl.w_alpha + i]; }
+  for (int i = t; i < 128; i += nt) side->bias_views[i] = params[pl.b_views + i];
+  for (int i = t; i < 3 * 128; i += nt) side->w_rgb[i / 128][i % 128] = params[pl.w_rgb + i];
+  if (t == 0) {
+    side->b_alpha = params[pl.b_alpha];
+    side->b_rgb[0] = params[pl.b_rgb]; side->b_rgb[1] = params[pl.b_rgb + 1]; side->b_rgb[2] = params[pl.b_rgb + 2];
+  }
+}
+
 __device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }

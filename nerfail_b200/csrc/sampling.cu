@@ -9,6 +9,7 @@
 // kernels is that the CDF, the binary search and the 192-way sort live in shared memory per ray instead
 // of the reference's expanded [R,128,63] gathers and a global sort.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace nfb {
 
@@ -369,6 +370,133 @@ hierarchical_kernel(const float* __restrict__ z_coarse, const float* __restrict_
   }
 }
 
+// ---- the lego shape (64 coarse depths, 128 new samples) with everything sized at compile time ------------------------
+// Same arithmetic, same results as hierarchical_kernel (tests/test_gpu_kernels.py compares them bit for bit); what changes
+// is the instruction count per ray (1920 -> ~1100 warp instructions, the kernel is issue-bound):
+//   * searches are unrolled descents without bound checks: 63 knots = 32+16+8+4+2+1, so lo + step never leaves the
+//     array; a 64- or 128-long run is one comparison with its last element plus a 6- / 7-step descent;
+//   * a new sample needs NO search to find its place among the coarse depths: it was interpolated between the bin edges
+//     mid[below] and mid[above], and mid[i] lies between z[i] and z[i+1], so "coarse depths <= sample" is below + 1 plus at
+//     most a couple of comparisons (kept as a loop, so it stays correct for any rounding);
+//   * loop trip counts (2 or 4 per lane) are constants, the shared-memory windows are fixed offsets.
+template <int SC, int N>
+__device__ __forceinline__ int count_less_unrolled(uint32_t arr, float v) {       // number of arr[0..N) strictly below v
+  static_assert((N & (N - 1)) == 0, "power of two");
+  if (lds_f32(arr + 4 * (N - 1)) < v) return N;
+  int lo = 0;
+#pragma unroll
+  for (int step = N >> 1; step > 0; step >>= 1)
+    if (lds_f32(arr + 4 * (lo + step - 1)) < v) lo += step;
+  return lo;
+}
+
+template <int SC, int N>
+__global__ void __launch_bounds__(128)
+hierarchical_fixed_kernel(const float* __restrict__ z_coarse, const float* __restrict__ weights,
+                          const float* __restrict__ u, const Rng rng, int R,
+                          float* __restrict__ z_fine, float* __restrict__ z_samples, float* __restrict__ z_std) {
+  constexpr int NB = SC - 1, SF = SC + N, PER_WARP = 2 * NB + SC + N + SF;
+  static_assert(NB == 63 && (N & (N - 1)) == 0, "built for 64 coarse depths and a power-of-two sample count");
+  __shared__ float smem[4 * PER_WARP];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* cdf = smem + wib * PER_WARP;
+  float* sb = cdf + NB;
+  float* zc = sb + NB;
+  float* zs = zc + SC;
+  float* out = zs + N;
+  const uint32_t cdf_a = smem_addr(cdf), sb_a = smem_addr(sb), zc_a = smem_addr(zc), zs_a = smem_addr(zs), out_a = smem_addr(out);
+  for (int r = blockIdx.x * 4 + wib; r < R; r += gridDim.x * 4) {
+#pragma unroll
+    for (int i = lane; i < SC; i += 32) zc[i] = __ldg(z_coarse + (int64_t)r * SC + i);
+    __syncwarp();
+#pragma unroll
+    for (int i = lane; i < NB; i += 32) sb[i] = __fmul_rn(0.5f, __fadd_rn(zc[i + 1], zc[i]));   // :392
+    build_cdf(weights + (int64_t)r * SC + 1, NB - 1, cdf, lane);                                // weights[...,1:-1]
+    float sum = 0.f;
+    int rank_c[N / 32];                        // coarse depths <= sample, per sample of this lane
+    float val[N / 32];
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) {
+      const int k = lane + 32 * j;
+      const float uk = u ? __ldg(u + (int64_t)r * N + k) : (rng.on ? philox_uniform(rng, 1u, (uint64_t)r * N + k) : linspace01(k, N));
+      int lo = 0;                              // torch.searchsorted(cdf, u, right=True): knots that are not > u
+#pragma unroll
+      for (int step = 32; step > 0; step >>= 1)
+        if (!(lds_f32(cdf_a + 4 * (lo + step - 1)) > uk)) lo += step;
+      const int below = max(0, lo - 1), above = min(NB - 1, lo);
+      const float c0 = lds_f32(cdf_a + 4 * below), c1 = lds_f32(cdf_a + 4 * above);
+      float denom = __fsub_rn(c1, c0);
+      if (denom < 1e-5f) denom = 1.f;
+      const float t = __fdiv_rn(__fsub_rn(uk, c0), denom);
+      const float b0 = lds_f32(sb_a + 4 * below), b1 = lds_f32(sb_a + 4 * above);
+      const float s = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+      zs[k] = s;
+      val[j] = s;
+      sum += s;
+      if (z_samples) z_samples[(int64_t)r * N + k] = s;
+      int c = below + 1;                       // z[below] <= mid[below] <= s; settle the few neighbours by comparison
+      while (c < SC && lds_f32(zc_a + 4 * c) <= s) ++c;
+      while (c > 0 && lds_f32(zc_a + 4 * (c - 1)) > s) --c;
+      rank_c[j] = c;
+    }
+    __syncwarp();
+    if (z_std) {   // torch.std(z_samples, -1, unbiased=False)
+      const float mean = warp_sum(sum) / (float)N;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < N / 32; ++j) { const float dlt = val[j] - mean; sq += dlt * dlt; }
+      sq = warp_sum(sq);
+      if (lane == 0) z_std[r] = sqrtf(sq / (float)N);
+    }
+    bool unsorted = false;
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) { const int k = lane + 32 * j; if (k + 1 < N) unsorted |= zs[k] > zs[k + 1]; }
+    unsorted = __any_sync(FULL, unsorted);
+    if (unsorted) {
+      // rare for deterministic u (isolated inversions at bin boundaries), the rule for random u: sort the new samples
+      // (bitonic network), then re-derive each sample's coarse rank; the rank merge below needs sorted runs
+      for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < N; i += 32) {
+            const int l = i ^ j;
+            if (l > i) {
+              const float a = zs[i], b = zs[l];
+              const bool asc = (i & k) == 0;
+              if ((a > b) == asc) { zs[i] = b; zs[l] = a; }
+            }
+          }
+          __syncwarp();
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < N / 32; ++j) {
+        const float v = zs[lane + 32 * j];
+        val[j] = v;
+        int c = 0;                             // number of coarse depths <= v
+        if (lds_f32(zc_a + 4 * (SC - 1)) <= v) c = SC;
+        else {
+#pragma unroll
+          for (int step = SC >> 1; step > 0; step >>= 1)
+            if (lds_f32(zc_a + 4 * (c + step - 1)) <= v) c += step;
+        }
+        rank_c[j] = c;
+      }
+    }
+    // merge by rank: coarse element i goes to i + (new samples strictly below it), sample k to k + (coarse depths <= it)
+#pragma unroll
+    for (int i = lane; i < SC; i += 32) {
+      const float v = lds_f32(zc_a + 4 * i);
+      sts_f32(out_a + 4 * (i + count_less_unrolled<SC, N>(zs_a, v)), v);
+    }
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) sts_f32(out_a + 4 * (lane + 32 * j + rank_c[j]), val[j]);
+    __syncwarp();
+#pragma unroll
+    for (int i = lane; i < SF; i += 32) z_fine[(int64_t)r * SF + i] = out[i];
+    __syncwarp();
+  }
+}
+
 static int grid_for(int64_t items, int per_block, int blocks_per_sm) {
   int64_t blocks = (items + per_block - 1) / per_block;
   int64_t cap = (int64_t)sm_count() * blocks_per_sm;
@@ -449,6 +577,13 @@ static int hierarchical_launch(const float* z_coarse, const float* weights, cons
   if (Sc < 3 || Sc > 128 || Sc + N > 512)
     return nfb::fail(NFB_E_UNSUPPORTED, "hierarchical: need 3 <= Sc <= 128 and Sc+N <= 512 (Sc=%d N=%d)", Sc, N);
   if (R == 0) return NFB_OK;
+  // the lego shape has its own compile-time-sized kernel; NERFAIL_B200_HIER=generic keeps the general one (cross-check)
+  const char* hier_env = getenv("NERFAIL_B200_HIER");
+  if (Sc == 64 && N == 128 && !(hier_env && hier_env[0] == 'g')) {
+    nfb::hierarchical_fixed_kernel<64, 128><<<nfb::grid_for(R, 4, 16), 128, 0, (cudaStream_t)stream>>>(
+        z_coarse, weights, u, rng, R, z_fine, z_samples, z_std);
+    return nfb::check_launch("hierarchical");
+  }
   int P = 1;
   while (P < N) P <<= 1;
   const size_t smem = (size_t)4 * (2 * (Sc - 1) + Sc + P + Sc + N) * sizeof(float);

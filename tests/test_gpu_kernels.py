@@ -453,3 +453,29 @@ def test_rays_from_batch_and_fused_mse_loss(cuda):
         l1, m1 = ops.MseLoss2Fn.apply(c, None, tgt.to(cuda))
         l1.backward()
         assert abs(float(l1) - float(torch.mean((rgb - tgt) ** 2))) <= 2e-6 and float(m1[1]) == 0.0
+
+
+def test_hierarchical_fixed_shape_kernel_equals_the_general_kernel(cuda, monkeypatch):
+    """The compile-time-sized kernel for the lego shape (64 coarse depths, 128 new samples; csrc/sampling.cu) against the
+    general one (NERFAIL_B200_HIER=generic), bit for bit: deterministic u, caller-provided random u, kernel-side Philox u;
+    flat, peaked and mostly-empty weight profiles (long runs of empty bins are where the search shortcuts could go wrong)."""
+    from nerfail_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    R = 1500
+    z = torch.sort(torch.rand(R, 64, generator=g) * 4 + 2, dim=-1).values
+    w = torch.rand(R, 64, generator=g) ** 6
+    w[:200] = 0.0                                            # flat pdf
+    w[200:400, 10:] = 0.0                                     # mass in the first bins only
+    w[400:600] = 0.0; w[400:600, 40] = 1.0                    # a single occupied bin
+    w[600:700] = torch.rand(100, 64, generator=g)             # broad
+    z[700:720] = torch.linspace(2, 6, 64)                     # the reference's own deterministic coarse depths
+    u = torch.rand(R, 128, generator=g)
+    zc, wc, uc = z.to(cuda), w.to(cuda), u.to(cuda)
+    for kwargs in (dict(u=None), dict(u=uc), dict(u=None, rng=(123, 9))):
+        monkeypatch.delenv("NERFAIL_B200_HIER", raising=False)
+        a = ops.hierarchical(zc, wc, 128, **kwargs)
+        monkeypatch.setenv("NERFAIL_B200_HIER", "generic")
+        b = ops.hierarchical(zc, wc, 128, **kwargs)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y), kwargs
+        assert bool((a[0][:, 1:] >= a[0][:, :-1]).all())

@@ -96,6 +96,35 @@ def test_fused_mlp_is_deterministic_and_repacks_on_update(cuda):
     assert torch.equal(c[..., 3], a[..., 3])
 
 
+def test_fused_pack_kernel_equals_the_two_specification_kernels(cuda, monkeypatch):
+    """nfb_mlp_update packs both weight images with one 16-bytes-per-thread kernel; NERFAIL_B200_PACK=split selects the two
+    one-element-per-thread kernels that spell the layouts out.  Same bits: the inference output and, through the training
+    kernels (which read the transposed image), every parameter gradient are identical."""
+    import nerfail_b200 as nb
+    from nerfail_b200 import ops
+    monkeypatch.setenv("NERFAIL_B200_TRAIN", "bf16")
+    pts, dirs = _inputs(11, 200, 3)
+    rays = torch.cat([torch.zeros(200, 3), torch.randn(200, 3), 2 * torch.ones(200, 1), 6 * torch.ones(200, 1),
+                      torch.nn.functional.normalize(torch.randn(200, 3), dim=-1)], -1).to(cuda)
+    z = torch.sort(torch.rand(200, 8) * 4 + 2, dim=-1).values.to(cuda)
+    outs = []
+    for mode in ("fused", "split"):
+        monkeypatch.setenv("NERFAIL_B200_PACK", mode)
+        net = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
+        net.load_state_dict(synth.make_non_degenerate(synth.random_state_dict(5), 5))
+        with torch.no_grad():
+            raw = net.fused().forward_points(pts.to(cuda), dirs.to(cuda))
+        torch.manual_seed(0)
+        tr = net.forward_rays_train(rays, z)
+        (tr * torch.linspace(-1, 1, tr.numel(), device=cuda).reshape(tr.shape)).sum().backward()
+        net.fused().status()
+        outs.append((raw, tr.detach(), [p.grad.clone() for p in net.ordered_params()]))
+    (ra, ta, ga), (rb, tb, gb) = outs
+    assert torch.equal(ra, rb) and torch.equal(ta, tb)
+    for a, b in zip(ga, gb):          # the weight gradients are accumulated with L2 float reductions: order-dependent in the last bits
+        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-12
+
+
 def test_fp32_mlp_forward_vs_reference_golden(cuda):
     import nerfail_b200 as nb
     g = golden("mlp.npz")
