@@ -708,7 +708,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
         const float next_bias = bias_elem(last ? 0 : s + 1);      // consumed after this step's drain (latency hidden)
         if (s < 9) {
           const bool relu = (s < 8);
-          float sig_acc = 0.f;
+          float sig_acc = 0.f, sig_b = 0.f, sig_c = 0.f, sig_d = 0.f;     // four partial sums: a 32-deep FFMA chain per drain iteration sat on step 7's critical path
 #pragma unroll 1
           for (int cc = 0; cc < 4; ++cc) {             // 4 x 32 accumulator columns of this thread's half
             const int col0 = hcol * 128 + cc * 32;
@@ -731,9 +731,9 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
               for (int j = 0; j < 8; ++j) {
                 const float4 w4 = reinterpret_cast<const float4*>(sd->w_alpha + col0)[j];
                 sig_acc = fmaf(fmaxf(h[4 * j], 0.f), w4.x, sig_acc);
-                sig_acc = fmaf(fmaxf(h[4 * j + 1], 0.f), w4.y, sig_acc);
-                sig_acc = fmaf(fmaxf(h[4 * j + 2], 0.f), w4.z, sig_acc);
-                sig_acc = fmaf(fmaxf(h[4 * j + 3], 0.f), w4.w, sig_acc);
+                sig_b = fmaf(fmaxf(h[4 * j + 1], 0.f), w4.y, sig_b);
+                sig_c = fmaf(fmaxf(h[4 * j + 2], 0.f), w4.z, sig_c);
+                sig_d = fmaf(fmaxf(h[4 * j + 3], 0.f), w4.w, sig_d);
               }
             }
             if (AUX && last && dbg_out) {
@@ -763,6 +763,7 @@ mlp_fused_fwd_kernel(const FwdArgs a) {
           // This warp's share of the next A operand is in shared memory: hand it over NOW.  What follows (the sigma
           // combine, the view-direction encoding, the refill of the bias row) touches neither the activation chunks nor,
           // before step 9, the encoding chunk the next MMA reads, so it runs beside that MMA instead of delaying it.
+          sig_acc = (sig_acc + sig_b) + (sig_c + sig_d);
           if (tracing && e == 0) trace_evt(2, 0x6000 | (s << 4) | g, clock64(), clock64(), 2);
           if (!last) signal_a_ready();
           if (tracing && e == 0) trace_evt(2, 0x4000 | (s << 4) | g, clock64(), clock64(), 0);

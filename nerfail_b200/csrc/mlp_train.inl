@@ -506,7 +506,7 @@ mlp_train_kernel(const TrainArgs a) {
           const uint32_t* mp = mask_tile + (mask_layer * 8 + hcol * 4) * 128 + row;
           mw4 = make_uint4(mp[0], mp[128], mp[256], mp[384]);
         }
-        float sig_acc = 0.f;
+        float sig_acc = 0.f, sig_b = 0.f, sig_c = 0.f, sig_d = 0.f;       // same four partial sums as the inference kernel (identical raw)
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           if (cc == 2) {
@@ -543,8 +543,8 @@ mlp_train_kernel(const TrainArgs a) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 w4 = reinterpret_cast<const float4*>(sd->w_alpha + col0)[j];
-                sig_acc = fmaf(fmaxf(h[4 * j], 0.f), w4.x, sig_acc); sig_acc = fmaf(fmaxf(h[4 * j + 1], 0.f), w4.y, sig_acc);
-                sig_acc = fmaf(fmaxf(h[4 * j + 2], 0.f), w4.z, sig_acc); sig_acc = fmaf(fmaxf(h[4 * j + 3], 0.f), w4.w, sig_acc);
+                sig_acc = fmaf(fmaxf(h[4 * j], 0.f), w4.x, sig_acc); sig_b = fmaf(fmaxf(h[4 * j + 1], 0.f), w4.y, sig_b);
+                sig_c = fmaf(fmaxf(h[4 * j + 2], 0.f), w4.z, sig_c); sig_d = fmaf(fmaxf(h[4 * j + 3], 0.f), w4.w, sig_d);
               }
             }
             if (relu) {
@@ -602,6 +602,7 @@ mlp_train_kernel(const TrainArgs a) {
                            pack_bf16(h[8 * u + 4], h[8 * u + 5]), pack_bf16(h[8 * u + 6], h[8 * u + 7]));
           }
         }
+        sig_acc = (sig_acc + sig_b) + (sig_c + sig_d);
         if (MODE == MODE_FWD && s == 8 && hcol == 0) {
           float f[64];
           encode3<L_DIR>(vx, vy, vz, f);

@@ -5,7 +5,10 @@ metrics the profile notes quote.  With --traffic <samples per launch> it also wr
 bench.py reads for roofline.traffic (dram__bytes_read.sum + dram__bytes_write.sum per sample of the fused MLP kernel)."""
 import csv, io, json, os, subprocess, sys
 
-args = [a for a in sys.argv[1:] if not a.startswith("--")]
+argv = list(sys.argv[1:])
+if "--traffic" in argv:
+    i = argv.index("--traffic"); del argv[i:i + 2]
+args = [a for a in argv if not a.startswith("--")]
 rep, prefix = args[0], args[1]
 regex = args[2] if len(args) > 2 else None
 cmd = ["ncu", "-i", rep, "--page", "raw", "--csv"]

@@ -438,3 +438,80 @@ def test_bf16_training_tracks_fp32_training_within_psnr_budget(cuda):
     # (0.05 dB against the oracle's training loop, several seeds) is tests/test_gpu_fullsize.py
     assert np.allclose(l16, l32, rtol=3e-2), (list(zip(l16, l32)))
     assert abs(p16 - p32) < 0.05, (p16, p32)
+
+
+def test_more_fused_networks_than_constant_memory_entries(cuda):
+    """Any number of fused networks may be alive per device: the four constant-memory entries that hold the head weights
+    are shared LRU (csrc/mlp_fused.cu: ensure_cslot).  Six networks rendered round-robin, twice, each against its own
+    first result; NeRF.close() releases a handle explicitly."""
+    import nerfail_b200 as nb
+    nets, firsts = [], []
+    pts = (torch.rand(300, 16, 3, generator=torch.Generator().manual_seed(1)) * 4 - 2).to(cuda)
+    dirs = torch.nn.functional.normalize(torch.randn(300, 3, generator=torch.Generator().manual_seed(2)), dim=-1).to(cuda)
+    with torch.no_grad():
+        for i in range(6):
+            n = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
+            n.load_state_dict(synth.make_non_degenerate(synth.random_state_dict(20 + i), 20 + i))
+            nets.append(n)
+            firsts.append(n.fused().forward_points(pts, dirs).clone())
+        for i in range(5):
+            assert not torch.equal(firsts[i], firsts[i + 1])
+        for _ in range(2):
+            for i in (5, 0, 3, 1, 4, 2):
+                assert torch.equal(nets[i].fused().forward_points(pts, dirs), firsts[i]), i
+        for n in nets:
+            n.fused().status()
+        nets[0].close()
+        assert nets[0]._fused is None
+        assert torch.equal(nets[0].fused().forward_points(pts, dirs), firsts[0])
+
+
+def test_embedder_gradient_and_out_of_range_sampler_shapes(cuda, fp32_mode):
+    """(1) The drop-in Embedder is differentiable w.r.t. its inputs like the reference's (run_nerf_helpers.py:36-50) — pose /
+    ray optimisation through run_network keeps its gradient — and refuses the in-place form that would silently drop it.
+    (2) Shapes outside the fused hierarchical kernel fall back to the reference's own sequence on the sample_pdf kernel
+    (N_samples > 128), and sample_pdf itself handles bin counts beyond one 48 KB shared-memory window."""
+    import nerfail_b200 as nb
+    from nerfail_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(50, 3, generator=g) * 2 - 1)
+    e10, _ = nb.get_embedder(10)
+    a = x.clone().to(cuda).requires_grad_(True)
+    out = e10(a)
+    cot = torch.randn(50, 63, generator=g)
+    (out * cot.to(cuda)).sum().backward()
+    b = x.clone().requires_grad_(True)
+    (no.positional_encoding(b, 10) * cot).sum().backward()
+    assert float((a.grad.cpu() - b.grad).abs().max()) <= 1e-3 * float(b.grad.abs().max())
+    with pytest.raises(RuntimeError, match="not differentiable"):
+        e10.embed(a, torch.empty(50, 63, device=cuda), 0)
+    # gradient to the points through run_network (fp32 layer kernels)
+    net = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
+    sd = synth.make_non_degenerate(synth.random_state_dict(0), 0)
+    net.load_state_dict(sd)
+    e4, _ = nb.get_embedder(4)
+    pts = (torch.rand(6, 5, 3, generator=g) * 2 - 1)
+    dirs = torch.nn.functional.normalize(torch.randn(6, 3, generator=g), dim=-1)
+    pg = pts.clone().to(cuda).requires_grad_(True)
+    raw = nb.run_network(pg, dirs.to(cuda), net, e10, e4)
+    raw.sum().backward()
+    pc = pts.clone().requires_grad_(True)
+    no.query_network(sd, pc, dirs).sum().backward()
+    assert pg.grad is not None and float((pg.grad.cpu() - pc.grad).abs().max()) <= 2e-3 * float(pc.grad.abs().max())
+    # sampler shapes
+    bins = torch.sort(torch.rand(9, 2000, generator=g) * 4 + 2, dim=-1).values
+    w = torch.rand(9, 1999, generator=g)
+    got = ops.sample_pdf(bins.to(cuda), w.to(cuda), 64).cpu()
+    want = no.inverse_cdf_samples(bins, w, 64)
+    assert float((got - want).abs().max()) <= 1e-4
+    K, _ = synth.intrinsics(8, 8)
+    rays = no.camera_rays(8, 8, K, torch.tensor(synth.pose_spherical(30.0, -30.0, 4.0)[:3, :4]), 2.0, 6.0)
+    sd_f = synth.make_non_degenerate(synth.random_state_dict(1), 1)
+    fine = nb.NeRF(D=8, W=256, input_ch=63, output_ch=5, skips=[4], input_ch_views=27, use_viewdirs=True).to(cuda)
+    fine.load_state_dict(sd_f)
+    with torch.no_grad():
+        ret = nb.render_rays(rays.to(cuda), net, nb.NetworkQuery(e10, e4, 1 << 16), 160, N_importance=32, network_fine=fine, white_bkgd=True)
+        ref = no.render_ray_batch(rays, sd, sd_f, 160, 32, True)
+    assert float((ret["rgb0"].cpu() - ref["rgb0"]).abs().max()) <= 1e-3
+    err = (ret["rgb_map"].cpu() - ref["rgb_map"]).abs().max(-1).values
+    assert float((err <= 1e-3).float().mean()) >= 0.9 and float(err.max()) <= 1e-2
