@@ -107,16 +107,23 @@ attack_exchange_kernel(PeerPtrs p, const float4* __restrict__ init, int64_t T, f
   for (int64_t r = row0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < row1; r += (int64_t)gridDim.x * blockDim.x) {
     float4 t = mine[r];
     if (!(t.w > 0.f)) continue;                       // inactive point: the update multiplies by (A > 0), nothing moves
+    // all G partial gradients of the row are requested before the first is used (one NVLink round trip per row instead of
+    // G dependent ones), then summed in rank order: every row has exactly one owner -> deterministic
+    float4 gq[MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q)
+      if (q < p.G) gq[q] = ld_peer4(reinterpret_cast<const float4*>(p.grad[q]) + r);
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    for (int q = 0; q < p.G; ++q) {                   // fixed rank order: every row has exactly one owner -> deterministic
-      const float4 g = ld_peer4(reinterpret_cast<const float4*>(p.grad[q]) + r);
-      gx += g.x; gy += g.y; gz += g.z;
-    }
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q)
+      if (q < p.G) { gx += gq[q].x; gy += gq[q].y; gz += gq[q].z; }
     const float4 t0 = __ldg(init + r);
     t.x = fmaxf(fminf(t.x - step * sgn(gx), t0.x + eps), t0.x - eps);
     t.y = fmaxf(fminf(t.y - step * sgn(gy), t0.y + eps), t0.y - eps);
     t.z = fmaxf(fminf(t.z - step * sgn(gz), t0.z + eps), t0.z - eps);
-    for (int q = 0; q < p.G; ++q) st_peer4(reinterpret_cast<float4*>(p.value[q]) + r, t);
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q)
+      if (q < p.G) st_peer4(reinterpret_cast<float4*>(p.value[q]) + r, t);
   }
   peer_end(p, epoch, epoch_ctr, cta_counter, status);
 }
@@ -138,11 +145,14 @@ adam_exchange_kernel(PeerPtrs p, float* __restrict__ exp_avg, float* __restrict_
   float4* m4 = reinterpret_cast<float4*>(exp_avg);
   float4* v4 = reinterpret_cast<float4*>(exp_avg_sq);
   for (int64_t i = q0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < q1; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 gq[MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q)
+      if (q < p.G) gq[q] = ld_peer4(reinterpret_cast<const float4*>(p.grad[q]) + i);
     float g[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int q = 0; q < p.G; ++q) {
-      const float4 x = ld_peer4(reinterpret_cast<const float4*>(p.grad[q]) + i);
-      g[0] += x.x; g[1] += x.y; g[2] += x.z; g[3] += x.w;
-    }
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q)
+      if (q < p.G) { g[0] += gq[q].x; g[1] += gq[q].y; g[2] += gq[q].z; g[3] += gq[q].w; }
     float4 w = mine[i], m = m4[i], v = v4[i];
     float* wp = &w.x; float* mp = &m.x; float* vp = &v.x;
 #pragma unroll
@@ -154,7 +164,9 @@ adam_exchange_kernel(PeerPtrs p, float* __restrict__ exp_avg, float* __restrict_
       wp[k] = wp[k] - step_size * (mp[k] / denom);
     }
     m4[i] = m; v4[i] = v;
-    for (int q = 0; q < p.G; ++q) st_peer4(reinterpret_cast<float4*>(p.value[q]) + i, w);
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q)
+      if (q < p.G) st_peer4(reinterpret_cast<float4*>(p.value[q]) + i, w);
   }
   peer_end(p, epoch, epoch_ctr, cta_counter, status);
 }

@@ -419,7 +419,9 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w, y = ctx.saved_tensors
-        dy = dy if (dy.stride(1) == 1 or dy.shape[1] == 1) else dy.contiguous()
+        # rows must be contiguous and the row pitch real: an expanded gradient (e.g. from .sum().backward()) has pitch 0
+        if not ((dy.stride(1) == 1 or dy.shape[1] == 1) and (dy.shape[0] <= 1 or dy.stride(0) >= dy.shape[1])):
+            dy = dy.contiguous()
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = linear_bwd_data(dy, y, ctx.relu, w)
