@@ -97,33 +97,50 @@ __device__ __forceinline__ void peer_end(const PeerPtrs& p, uint32_t epoch, uint
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }   // torch.sign
 
 // attack_NeRFail_S.py:348-392 across G GPUs: rows [row0, row1) of the [T,4] table are this rank's slice.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 attack_exchange_kernel(PeerPtrs p, const float4* __restrict__ init, int64_t T, float step, float eps,
                        uint32_t* epoch_ctr, unsigned int* cta_counter, int* status) {
   const uint32_t epoch = peer_begin(p, epoch_ctr, status);
   const int64_t per = (T + p.G - 1) / p.G;
   const int64_t row0 = per * p.rank, row1 = min(T, row0 + per);
   float4* mine = reinterpret_cast<float4*>(p.value[p.rank]);
-  for (int64_t r = row0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < row1; r += (int64_t)gridDim.x * blockDim.x) {
-    float4 t = mine[r];
-    if (!(t.w > 0.f)) continue;                       // inactive point: the update multiplies by (A > 0), nothing moves
-    // all G partial gradients of the row are requested before the first is used (one NVLink round trip per row instead of
-    // G dependent ones), then summed in rank order: every row has exactly one owner -> deterministic
-    float4 gq[MAX_PEERS];
+  // Two rows per thread and iteration, every load of both rows in flight before the first use: the kernel is bound by the
+  // latency of its dependent loads (table row -> peers' gradients), not by bandwidth.
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = row0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < row1; r += 2 * stride) {
+    const int64_t rr[2] = {r, r + stride};
+    float4 t[2];
+    bool act[2];
 #pragma unroll
-    for (int q = 0; q < MAX_PEERS; ++q)
-      if (q < p.G) gq[q] = ld_peer4(reinterpret_cast<const float4*>(p.grad[q]) + r);
-    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      act[u] = rr[u] < row1;
+      t[u] = act[u] ? mine[rr[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      act[u] = act[u] && (t[u].w > 0.f);              // inactive point: the update multiplies by (A > 0), nothing moves
+    }
+    float4 gq[2][MAX_PEERS], t0[2];
 #pragma unroll
-    for (int q = 0; q < MAX_PEERS; ++q)
-      if (q < p.G) { gx += gq[q].x; gy += gq[q].y; gz += gq[q].z; }
-    const float4 t0 = __ldg(init + r);
-    t.x = fmaxf(fminf(t.x - step * sgn(gx), t0.x + eps), t0.x - eps);
-    t.y = fmaxf(fminf(t.y - step * sgn(gy), t0.y + eps), t0.y - eps);
-    t.z = fmaxf(fminf(t.z - step * sgn(gz), t0.z + eps), t0.z - eps);
+    for (int u = 0; u < 2; ++u) {
+      if (!act[u]) continue;
+      t0[u] = __ldg(init + rr[u]);
 #pragma unroll
-    for (int q = 0; q < MAX_PEERS; ++q)
-      if (q < p.G) st_peer4(reinterpret_cast<float4*>(p.value[q]) + r, t);
+      for (int q = 0; q < MAX_PEERS; ++q)
+        if (q < p.G) gq[u][q] = ld_peer4(reinterpret_cast<const float4*>(p.grad[q]) + rr[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!act[u]) continue;
+      float gx = 0.f, gy = 0.f, gz = 0.f;             // rank order; every row has exactly one owner -> deterministic
+#pragma unroll
+      for (int q = 0; q < MAX_PEERS; ++q)
+        if (q < p.G) { gx += gq[u][q].x; gy += gq[u][q].y; gz += gq[u][q].z; }
+      float4 o = t[u];
+      o.x = fmaxf(fminf(o.x - step * sgn(gx), t0[u].x + eps), t0[u].x - eps);
+      o.y = fmaxf(fminf(o.y - step * sgn(gy), t0[u].y + eps), t0[u].y - eps);
+      o.z = fmaxf(fminf(o.z - step * sgn(gz), t0[u].z + eps), t0[u].z - eps);
+#pragma unroll
+      for (int q = 0; q < MAX_PEERS; ++q)
+        if (q < p.G) st_peer4(reinterpret_cast<float4*>(p.value[q]) + rr[u], o);
+    }
   }
   peer_end(p, epoch, epoch_ctr, cta_counter, status);
 }
@@ -269,9 +286,9 @@ int nfb_peer_status(const nfb_peer_t* h) {
   return NFB_OK;
 }
 
-static int exchange_grid(int64_t items) {
+static int exchange_grid(int64_t items, int ctas_per_sm = 4) {
   int64_t blocks = (items + 255) / 256;
-  const int64_t cap = (int64_t)nfb::sm_count() * 4;
+  const int64_t cap = (int64_t)nfb::sm_count() * ctas_per_sm;
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }
@@ -282,7 +299,7 @@ int nfb_attack_exchange_step(nfb_peer_t* h, const float* init, int64_t T, float 
   int rc = nfb_peer_status(h);
   if (rc != NFB_OK) return rc;
   const int64_t per = (T + h->ptrs.G - 1) / h->ptrs.G;
-  nfb::attack_exchange_kernel<<<exchange_grid(per), 256, 0, (cudaStream_t)stream>>>(
+  nfb::attack_exchange_kernel<<<exchange_grid((per + 1) / 2, 2), 256, 0, (cudaStream_t)stream>>>(      // two rows per thread, 2 CTAs per SM resident
       h->ptrs, reinterpret_cast<const float4*>(init), T, signed_step, eps, h->epoch_ctr, h->cta_counter, h->status_dev);
   return nfb::check_launch("attack_exchange_step");
 }
