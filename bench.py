@@ -12,11 +12,16 @@ slowest rank's device time.
 Keys beyond the base contract:
   roofline      the fused MLP kernel (tensor-bound): algorithmic FLOP/launch / CUDA-event duration vs the measured
                 bf16 peak of MEASURED_PEAKS.json (sustained figure — the kernel is timed inside a long step)
-  cpu_baseline  the oracle port of the reference's render path, timed on this box's host cores on a bounded sample
+                roofline.traffic = dram bytes per launch from the committed ncu capture (profiles/r02_mlp_traffic.json)
+  cpu_baseline  the reference's own CPU render path on this box's host cores, bounded sample: the UNMODIFIED reference
+                staged under oracle/_ref (kind "reference"), or the oracle port if that directory is missing (kind "port")
   e2e           the same metric through the public nerfail_b200.render() with host inputs (pose, intrinsics) and
                 the result images copied back to pinned host memory inside the timed region
---impl reference times the reference's CPU implementation (oracle port; the reference is a Python program whose
-source tree does not travel to the GPU box) on the same workload, bounded sample per step.
+  strong        the two strong-scaling workloads with a real exchange: attack iteration of 100 views (config 3) and
+                retraining step of 4096 rays (config 5), ms per iteration at this N (also under config.strong_scaling_ms)
+  extra         the other BASELINE configs in detail (attack iteration, retraining step, 8-NN, view sweep, loader, ...)
+--impl reference times the reference's CPU implementation (oracle/_ref: the unmodified run_nerf.render()) on the same
+workload, bounded sample per step; rank 0 only.
 """
 from __future__ import annotations
 
@@ -708,6 +713,9 @@ def main():
                               "attack_ms_nccl": extra["attack_iteration"]["ms_per_iteration_nccl_allreduce_then_update"],
                               "train_ms_nccl": extra["retraining_step"]["cuda_graph_step_with_adam"]["ms_per_step"],
                               "knn_views_per_s": extra["knn_sweep"]["value"]}
+            # the same two figures inside a key every record keeps whole
+            line["config"]["strong_scaling_ms"] = {"attack_iteration_100_views": round(line["strong"]["attack_ms"], 4),
+                                                   "retraining_step_4096_rays": round(line["strong"]["train_ms"], 4)}
             if ms_strict is not None:
                 extra["render_strict_chunk_1024"] = {"metric": "render rays/s with literal 1024-ray chunks (625 passes per view, NERFAIL_B200_STRICT_CHUNK=1)",
                                                      "value": n_rays / (ms_strict / 1e3), "unit": "rays/s", "ms_per_view": ms_strict,
