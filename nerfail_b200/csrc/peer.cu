@@ -97,29 +97,31 @@ __device__ __forceinline__ void peer_end(const PeerPtrs& p, uint32_t epoch, uint
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }   // torch.sign
 
 // attack_NeRFail_S.py:348-392 across G GPUs: rows [row0, row1) of the [T,4] table are this rank's slice.
-__global__ void __launch_bounds__(256, 2)
+template <int U>          // rows per thread and iteration: 2 with peers (NVLink latency), 1 without (plain bandwidth)
+__global__ void __launch_bounds__(256, U == 2 ? 2 : 3)
 attack_exchange_kernel(PeerPtrs p, const float4* __restrict__ init, int64_t T, float step, float eps,
                        uint32_t* epoch_ctr, unsigned int* cta_counter, int* status) {
   const uint32_t epoch = peer_begin(p, epoch_ctr, status);
   const int64_t per = (T + p.G - 1) / p.G;
   const int64_t row0 = per * p.rank, row1 = min(T, row0 + per);
   float4* mine = reinterpret_cast<float4*>(p.value[p.rank]);
-  // Two rows per thread and iteration, every load of both rows in flight before the first use: the kernel is bound by the
-  // latency of its dependent loads (table row -> peers' gradients), not by bandwidth.
+  // U rows per thread and iteration, every load of all of them in flight before the first use: with peers the kernel is
+  // bound by the latency of its dependent loads (table row -> peers' gradients), not by bandwidth.
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t r = row0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < row1; r += 2 * stride) {
-    const int64_t rr[2] = {r, r + stride};
-    float4 t[2];
-    bool act[2];
+  for (int64_t r = row0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < row1; r += U * stride) {
+    int64_t rr[U];
+    float4 t[U];
+    bool act[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
+      rr[u] = r + u * stride;
       act[u] = rr[u] < row1;
       t[u] = act[u] ? mine[rr[u]] : make_float4(0.f, 0.f, 0.f, 0.f);
       act[u] = act[u] && (t[u].w > 0.f);              // inactive point: the update multiplies by (A > 0), nothing moves
     }
-    float4 gq[2][MAX_PEERS], t0[2];
+    float4 gq[U][MAX_PEERS], t0[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (!act[u]) continue;
       t0[u] = __ldg(init + rr[u]);
 #pragma unroll
@@ -127,7 +129,7 @@ attack_exchange_kernel(PeerPtrs p, const float4* __restrict__ init, int64_t T, f
         if (q < p.G) gq[u][q] = ld_peer4(reinterpret_cast<const float4*>(p.grad[q]) + rr[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (!act[u]) continue;
       float gx = 0.f, gy = 0.f, gz = 0.f;             // rank order; every row has exactly one owner -> deterministic
 #pragma unroll
@@ -299,8 +301,12 @@ int nfb_attack_exchange_step(nfb_peer_t* h, const float* init, int64_t T, float 
   int rc = nfb_peer_status(h);
   if (rc != NFB_OK) return rc;
   const int64_t per = (T + h->ptrs.G - 1) / h->ptrs.G;
-  nfb::attack_exchange_kernel<<<exchange_grid((per + 1) / 2, 2), 256, 0, (cudaStream_t)stream>>>(      // two rows per thread, 2 CTAs per SM resident
-      h->ptrs, reinterpret_cast<const float4*>(init), T, signed_step, eps, h->epoch_ctr, h->cta_counter, h->status_dev);
+  if (h->ptrs.G > 1)      // two rows per thread, 2 CTAs per SM resident
+    nfb::attack_exchange_kernel<2><<<exchange_grid((per + 1) / 2, 2), 256, 0, (cudaStream_t)stream>>>(
+        h->ptrs, reinterpret_cast<const float4*>(init), T, signed_step, eps, h->epoch_ctr, h->cta_counter, h->status_dev);
+  else
+    nfb::attack_exchange_kernel<1><<<exchange_grid(per, 3), 256, 0, (cudaStream_t)stream>>>(
+        h->ptrs, reinterpret_cast<const float4*>(init), T, signed_step, eps, h->epoch_ctr, h->cta_counter, h->status_dev);
   return nfb::check_launch("attack_exchange_step");
 }
 
