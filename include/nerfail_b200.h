@@ -117,6 +117,8 @@ NFB_API int nfb_mlp_fwd(const nfb_mlp_t* h, int mode, const float* pts, const fl
  * LRU (a network that lost its entry re-acquires one at its next launch; that costs one host-side wait). */
 NFB_API int nfb_mlp_status(nfb_mlp_t* h);
 NFB_API int nfb_mlp_poll(const nfb_mlp_t* h);
+/* Test hook: raises the flag from the host exactly as a timed-out barrier wait does (no kernel involved). */
+NFB_API int nfb_mlp_debug_raise_abort(nfb_mlp_t* h);
 /* Validation entry: run only the first nsteps (1..10) MMA steps of the fused kernel and dump the fp32
  * post-activation values of the last executed step to dbg [R*S,256] (128 columns for the view layer).     */
 NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs,

@@ -37,6 +37,7 @@ SIGNATURES = {
     "nfb_mlp_fwd": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr]),
     "nfb_mlp_status": (c_int, [c_ptr]),
     "nfb_mlp_poll": (c_int, [c_ptr]),
+    "nfb_mlp_debug_raise_abort": (c_int, [c_ptr]),
     "nfb_mlp_fwd_debug": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_int, c_ptr, c_ptr]),
     "nfb_mlp_train_tiles": (c_i64, [c_i64]),
     "nfb_mlp_fwd_train": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),

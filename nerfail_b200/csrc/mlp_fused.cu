@@ -1060,6 +1060,14 @@ int nfb_mlp_poll(const nfb_mlp_t* h) {
   return refuse_if_aborted(h, "mlp_poll");
 }
 
+// Test hook: raise the time-out flag from the host (what a kernel does when a barrier wait expires), so the reporting
+// contract — launches refuse, nfb_mlp_poll reports, nfb_mlp_status reports and clears — can be exercised without a hang.
+int nfb_mlp_debug_raise_abort(nfb_mlp_t* h) {
+  NFB_REQUIRE(h && h->abort_host, "mlp_debug_raise_abort: null handle");
+  *h->abort_host = 1;
+  return NFB_OK;
+}
+
 static int mlp_launch(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs, const float* rays,
                       const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg, void* stream,
                       unsigned long long* trace = nullptr) {

@@ -515,3 +515,37 @@ def test_embedder_gradient_and_out_of_range_sampler_shapes(cuda, fp32_mode):
     assert float((ret["rgb0"].cpu() - ref["rgb0"]).abs().max()) <= 1e-3
     err = (ret["rgb_map"].cpu() - ref["rgb_map"]).abs().max(-1).values
     assert float((err <= 1e-3).float().mean()) >= 0.9 and float(err.max()) <= 1e-2
+
+
+def test_barrier_timeout_is_reported_on_the_product_paths(cuda, monkeypatch):
+    """A pipeline-barrier time-out inside a fused kernel must not silently poison later results (the kernel bails out with
+    invalid output and raises a flag).  With the flag raised through the test hook: every launch of that network refuses to
+    run, render() and train_step() raise, poll() reports without clearing, status() reports once and clears, and the
+    network works again afterwards."""
+    import nerfail_b200 as nb
+    from nerfail_b200 import _lib
+    monkeypatch.setenv("NERFAIL_B200_TRAIN", "bf16")
+    kw_train, kw, _, _, opt = nb.create_nerf(Args(), device=cuda)
+    H = W = 16
+    K, _ = synth.intrinsics(H, W)
+    c2w = torch.tensor(synth.pose_spherical(30.0, -30.0, 4.0)[:3, :4])
+    with torch.no_grad():
+        ok = nb.render(H, W, K, chunk=1024, c2w=c2w, near=2., far=6., **kw)[0].clone()
+    fused = kw["network_fine"].fused()
+    assert _lib.load().nfb_mlp_debug_raise_abort(fused._h) == 0
+    with pytest.raises(RuntimeError, match="time-out"):
+        fused.poll()
+    with pytest.raises(RuntimeError, match="time-out"):
+        fused.poll()                                              # sticky: polling does not clear
+    with torch.no_grad(), pytest.raises(RuntimeError, match="time-out"):
+        nb.render(H, W, K, chunk=1024, c2w=c2w, near=2., far=6., **kw)
+    rays = torch.stack([torch.zeros(64, 3), torch.nn.functional.normalize(torch.randn(64, 3), dim=-1)], 0).to(cuda)
+    with pytest.raises(RuntimeError, match="time-out"):
+        nb.train_step(rays, torch.rand(64, 3, device=cuda), H, W, K, 1024, dict(kw_train, near=2., far=6.), opt, 5e-4, 250, 0)
+    with pytest.raises(RuntimeError, match="timed out"):
+        fused.status()                                            # reports ...
+    fused.status()                                                # ... and clears
+    fused.poll()
+    with torch.no_grad():
+        again = nb.render(H, W, K, chunk=1024, c2w=c2w, near=2., far=6., **kw)[0]
+    assert torch.equal(ok, again)
