@@ -117,7 +117,8 @@ def _run_training(rank, world, dev):
     from nerfail_b200 import train as ntrain
     from oracle import synth
     from test_gpu_render import Args
-    os.environ["NERFAIL_B200_TRAIN"] = "bf16"
+    prev_train = os.environ.get("NERFAIL_B200_TRAIN")
+    os.environ["NERFAIL_B200_TRAIN"] = "bf16"          # restored at the end: world size 1 runs inside the pytest process
     H = W = 32
     K, _ = synth.intrinsics(H, W)
     poses = np.stack(synth.camera_ring(3)).astype(np.float32)
@@ -153,9 +154,15 @@ def _run_training(rank, world, dev):
         print(f"[rank {rank}] training mode {mode} ok", flush=True)
         return sd, losses
 
-    sd_a, l_a = run("nccl")
-    sd_b, l_b = run("peer")
-    sd_c, l_c = run("graph")
+    try:
+        sd_a, l_a = run("nccl")
+        sd_b, l_b = run("peer")
+        sd_c, l_c = run("graph")
+    finally:
+        if prev_train is None:
+            os.environ.pop("NERFAIL_B200_TRAIN", None)
+        else:
+            os.environ["NERFAIL_B200_TRAIN"] = prev_train
     assert np.allclose(l_a, l_b, rtol=2e-3), (l_a, l_b)
     assert np.allclose(l_a, l_c[:3], rtol=2e-3), (l_a, l_c)
     ref0 = synth.flat_params(synth.make_non_degenerate(synth.random_state_dict(0), 0))
