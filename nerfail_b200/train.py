@@ -185,6 +185,32 @@ class GraphedTrainStep:
         return self.out
 
 
+def make_train_stepper(n_rays: int, H: int, W: int, K, chunk: int, render_kwargs_train: dict, optimizer, lrate: float,
+                       lrate_decay: int, near: Optional[float] = None, far: Optional[float] = None, device=None,
+                       graph: bool = True, peer: Optional[bool] = None):
+    """The recommended way to run the optimisation loop of run_nerf.py:776-800: returns `step(batch_rays, target_s, global_step)
+    -> {'loss', 'psnr', 'psnr0'}` and the PeerAdam object (or None).
+    Under torch.distributed (world size > 1, one process per GPU of a node) the gradient average, Adam and the parameter
+    broadcast are the fused peer-memory kernel (dist.PeerAdam) unless peer=False keeps the NCCL all-reduces; graph=True
+    captures the whole step in one CUDA graph (GraphedTrainStep), which is what makes per-rank batches of a few hundred
+    rays worth sharding at all.  n_rays = this rank's share of the batch (sample_ray_batch(..., rank, world_size))."""
+    _, world_size = nd.world()
+    use_peer = (world_size > 1) if peer is None else bool(peer)
+    exchange = None
+    if use_peer:
+        nets = [render_kwargs_train.get("network_fn"), render_kwargs_train.get("network_fine")]
+        exchange = nd.PeerAdam(nets, optimizer, device)
+    if graph:
+        stepper = GraphedTrainStep(n_rays, H, W, K, chunk, render_kwargs_train, optimizer, lrate, lrate_decay, near, far,
+                                   device=device, exchange=exchange)
+        return stepper, exchange
+
+    def step(batch_rays, target_s, global_step):
+        return train_step(batch_rays, target_s, H, W, K, chunk, render_kwargs_train, optimizer, lrate, lrate_decay, global_step,
+                          near, far, exchange=exchange)
+    return step, exchange
+
+
 def save_checkpoint(path: str, global_step: int, render_kwargs_train: dict, optimizer) -> str:
     """The .tar of run_nerf.py:808-816 (same four keys), readable by the reference's and this package's create_nerf."""
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)

@@ -131,7 +131,7 @@ def _run_training(rank, world, dev):
         kw_train["network_fn"].load_state_dict(synth.make_non_degenerate(synth.random_state_dict(0), 0))
         kw_train["network_fine"].load_state_dict(synth.make_non_degenerate(synth.random_state_dict(1), 1))
         kws = dict(kw_train, near=2.0, far=6.0, perturb=0.0)        # deterministic sampling: nothing random between the runs
-        ex = nd.PeerAdam([kw_train["network_fn"], kw_train["network_fine"]], opt, dev) if mode != "nccl" else None
+        ex = nd.PeerAdam([kw_train["network_fn"], kw_train["network_fine"]], opt, dev) if mode == "peer" else None
         stepper = None
         rng = np.random.RandomState(0)
         losses = []
@@ -139,8 +139,9 @@ def _run_training(rank, world, dev):
             rays, tgt, _, _ = nb.sample_ray_batch(images, poses, [0, 1, 2], H, W, K, n_rand, i, 0, 0.5, rng=rng, device=dev,
                                                   rank=rank, world_size=world)
             if mode == "graph":
-                if stepper is None:
-                    stepper = ntrain.GraphedTrainStep(rays.shape[1], H, W, K, 32768, kws, opt, 5e-4, 250, device=dev, warmup=2, exchange=ex)
+                if stepper is None:     # the helper: CUDA graph + PeerAdam (peer=True also at world size 1: same kernels)
+                    stepper, ex = nb.make_train_stepper(rays.shape[1], H, W, K, 32768, kws, opt, 5e-4, 250, device=dev, peer=True)
+                    stepper.warmup = 2
                 out = stepper(rays, tgt, i)
             else:
                 out = nb.train_step(rays, tgt, H, W, K, 32768, kws, opt, 5e-4, 250, i, exchange=ex)
