@@ -251,6 +251,30 @@ NFB_API int nfb_render_rays_fwd(const nfb_mlp_t* coarse, const nfb_mlp_t* fine, 
                                 int perturb, uint64_t rng_seed, uint64_t rng_offset, float* rgb, float* disp, float* acc, float* rgb0, float* disp0, float* acc0, float* z_std,
                                 float* pts_max, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same ray batch UNDER AUTOGRAD (the optimisation step of run_nerf.py:776-791): forward that keeps what the backward
+ * needs, and the backward, one call each.
+ * replaces: render_rays (run_nerf.py:308-418) with requires_grad parameters + loss.backward() through it, for
+ * raw_noise_std = 0, N_importance > 0 and a separate fine network (the NeRFail configuration).
+ * nfb_render_rays_train_fwd: coarse depths -> training forward of the coarse network (saves bf16 activation images and
+ * relu masks) -> compositing -> resampling + merge (detached, :394) -> training forward of the fine network ->
+ * compositing.  Outputs as nfb_render_rays_fwd (no pts_max); raw of the fine pass (retraw) stays in the workspace at byte
+ * offset nfb_render_rays_train_raw_offset(...) as [R, N_samples + N_importance, 4].
+ * nfb_render_rays_bwd: from the gradients of the six images (any may be NULL = zero; a pass whose three are NULL is
+ * skipped) through compositing, the data-gradient chain and the grouped weight-gradient kernel of each network;
+ * ACCUMULATES into grad_coarse / grad_fine [nfb_mlp_param_count] in state_dict order (zero them once per step).
+ * The workspace (nfb_render_rays_train_workspace_bytes, 256-byte aligned, caller-owned) carries the saved state from the
+ * forward to the backward and must not be touched in between; ~10.6 KB per sample.                                   */
+NFB_API size_t nfb_render_rays_train_workspace_bytes(int R, int N_samples, int N_importance);
+NFB_API size_t nfb_render_rays_train_raw_offset(int R, int N_samples, int N_importance);
+NFB_API int nfb_render_rays_train_fwd(const nfb_mlp_t* coarse, const nfb_mlp_t* fine, const float* rays, int R, int N_samples,
+                                      int N_importance, int lindisp, int white_bkgd, const float* t_rand, const float* u,
+                                      float* rgb, float* disp, float* acc, float* rgb0, float* disp0, float* acc0, float* z_std,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+NFB_API int nfb_render_rays_bwd(const nfb_mlp_t* coarse, const nfb_mlp_t* fine, const float* rays, int R, int N_samples,
+                                int N_importance, int white_bkgd, const float* g_rgb, const float* g_disp, const float* g_acc,
+                                const float* g_rgb0, const float* g_disp0, const float* g_acc0, float* grad_coarse,
+                                float* grad_fine, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* B. GaussNet path                                                            */
 /* ------------------------------------------------------------------------- */

@@ -54,6 +54,12 @@ SIGNATURES = {
     "nfb_render_rays_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
     "nfb_render_rays_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
                                     c_int, C.c_uint64, C.c_uint64] + [c_ptr] * 8 + [c_ptr, C.c_size_t, c_ptr]),
+    "nfb_render_rays_train_workspace_bytes": (C.c_size_t, [c_int, c_int, c_int]),
+    "nfb_render_rays_train_raw_offset": (C.c_size_t, [c_int, c_int, c_int]),
+    "nfb_render_rays_train_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr] + [c_ptr] * 7
+                                  + [c_ptr, C.c_size_t, c_ptr]),
+    "nfb_render_rays_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int] + [c_ptr] * 6 + [c_ptr, c_ptr]
+                            + [c_ptr, C.c_size_t, c_ptr]),
     "nfb_attack_pack_rgb": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "nfb_attack_sign_step": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, C.c_float, C.c_float, c_ptr]),
     "nfb_rgba_to_chw": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, C.c_float, c_ptr, c_ptr]),

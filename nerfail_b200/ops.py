@@ -656,6 +656,76 @@ def render_rays_fused(coarse: "FusedMLP", fine: Optional["FusedMLP"], rays: torc
     return out
 
 
+class RenderRaysTrainFn(torch.autograd.Function):
+    """render_rays under autograd as TWO C calls: nfb_render_rays_train_fwd (coarse depths, training forward of the coarse
+    network, compositing, detached resampling, training forward of the fine network, compositing) and nfb_render_rays_bwd
+    (compositing backward, data-gradient chain and grouped weight gradient of each network).  The same kernels in the same
+    order as the per-op autograd path (NERFAIL_B200_RENDER_RAYS=ops), without ~50 Python-level launches per step.
+    Gradients flow to the two networks' parameters only (rays and depths are constants of the step, run_nerf.py:394).
+    Returns (rgb, disp, acc, rgb0, disp0, acc0, z_std, raw): z_std and raw are not differentiable."""
+
+    @staticmethod
+    def forward(ctx, net_c, net_f, rays, n_samples, n_importance, lindisp, white_bkgd, t_rand, u, *params):
+        lib = _lib.load()
+        fc, ff = net_c.fused(), net_f.fused()
+        rays = _f32(rays)
+        R = rays.shape[0]
+        dev = rays.device
+        Sf = n_samples + n_importance
+        f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+        rgb, disp, acc, rgb0, disp0, acc0, z_std = f(R, 3), f(R), f(R), f(R, 3), f(R), f(R), f(R)
+        nbytes = int(lib.nfb_render_rays_train_workspace_bytes(R, n_samples, n_importance))
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        t_rand = _f32(t_rand) if t_rand is not None else None
+        u = _f32(u) if u is not None else None
+        if R > 0:
+            with torch.cuda.device(dev):
+                check(lib.nfb_render_rays_train_fwd(fc._h, ff._h, ptr(rays), R, n_samples, n_importance, int(bool(lindisp)),
+                                                    int(bool(white_bkgd)), ptr(t_rand), ptr(u), ptr(rgb), ptr(disp), ptr(acc),
+                                                    ptr(rgb0), ptr(disp0), ptr(acc0), ptr(z_std), ptr(ws), nbytes, stream()),
+                      "nfb_render_rays_train_fwd")
+        off = int(lib.nfb_render_rays_train_raw_offset(R, n_samples, n_importance)) if R > 0 else 0
+        raw = ws[off:off + R * Sf * 16].view(torch.float32).view(R, Sf, 4)
+        ctx.nets, ctx.fused = (net_c, net_f), (fc, ff)
+        ctx.cfg = (R, n_samples, n_importance, bool(white_bkgd), nbytes)
+        ctx.n_c = len(net_c.ordered_params())
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.save_for_backward(rays, ws)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(z_std, raw)
+        return rgb, disp, acc, rgb0, disp0, acc0, z_std, raw
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc, g_rgb0, g_disp0, g_acc0, _g_std, _g_raw):
+        lib = _lib.load()
+        rays, ws = ctx.saved_tensors
+        R, n_samples, n_importance, white, nbytes = ctx.cfg
+        dev = rays.device
+        flats = []
+        for net, fused in zip(ctx.nets, ctx.fused):
+            sink = getattr(net, "_grad_sink", None)
+            if sink is not None:        # data-parallel: the flat gradient lives in NVLink peer memory (dist.PeerAdam)
+                sink.zero_()
+                flats.append(sink)
+            else:
+                flats.append(torch.zeros(fused.n_params, dtype=torch.float32, device=dev))
+        gs = [None if g is None else _f32(g) for g in (g_rgb, g_disp, g_acc, g_rgb0, g_disp0, g_acc0)]
+        if R > 0 and any(g is not None for g in gs):
+            with torch.cuda.device(dev):
+                check(lib.nfb_render_rays_bwd(ctx.fused[0]._h, ctx.fused[1]._h, ptr(rays), R, n_samples, n_importance, int(white),
+                                              ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(gs[3]), ptr(gs[4]), ptr(gs[5]),
+                                              ptr(flats[0]), ptr(flats[1]), ptr(ws), nbytes, stream()), "nfb_render_rays_bwd")
+        grads, k = [], 0
+        for i, shp in enumerate(ctx.shapes):        # views of the flat gradients in state_dict order: coarse first, then fine
+            if i == ctx.n_c:
+                k = 0
+            flat = flats[0] if i < ctx.n_c else flats[1]
+            n = math.prod(shp)
+            grads.append(flat[k:k + n].view(shp))
+            k += n
+        return (None,) * 9 + tuple(grads)
+
+
 class RgbaToChwFn(torch.autograd.Function):
     """Classifier input of model/GaussNet.py:121-145: [B,H,W,4] RGBA -> [B,3,H,W] RGB, `fill` where alpha (channel 3 of
     the image itself) is 0.  Backward = ChwToRgbaFn, whose backward is this op with fill 0: differentiable twice."""

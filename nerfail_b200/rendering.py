@@ -146,6 +146,33 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             t_rand = torch.tensor(np.random.rand(N_rays, N_samples), dtype=torch.float32, device=ray_batch.device)
         else:
             t_rand = torch.rand((N_rays, N_samples), device=ray_batch.device)
+    # Whole-batch training path: under autograd with the tensor-core training kernels, no noise and both networks present,
+    # the forward and the backward of this function are ONE C call each (nfb_render_rays_train_fwd / nfb_render_rays_bwd):
+    # the same kernels in the same order as the per-op path below, which NERFAIL_B200_RENDER_RAYS=ops keeps.
+    if (torch.is_grad_enabled() and raw_noise_std == 0. and N_importance > 0 and network_fine is not None and not with_pts_max
+            and ray_batch.shape[-1] == 11 and not ray_batch.requires_grad and nerf.train_precision() == "bf16"
+            and isinstance(network_query_fn, NetworkQuery)
+            and isinstance(network_query_fn.embed_fn, nerf.Embedder) and network_query_fn.embed_fn.multires == 10
+            and isinstance(network_query_fn.embeddirs_fn, nerf.Embedder) and network_query_fn.embeddirs_fn.multires == 4
+            and isinstance(network_fn, NeRF) and network_fn.fused_supported()
+            and isinstance(network_fine, NeRF) and network_fine.fused_supported() and network_fine is not network_fn
+            and 3 <= N_samples <= 128 and N_samples + N_importance <= 512 and N_rays > 0
+            and os.environ.get("NERFAIL_B200_RENDER_RAYS", "fused") != "ops"):
+        u = None
+        if perturb != 0.:
+            if pytest:
+                np.random.seed(0)
+                u = torch.tensor(np.random.rand(N_rays, N_importance), dtype=torch.float32, device=ray_batch.device)
+            else:
+                u = torch.rand((N_rays, N_importance), device=ray_batch.device)
+        rgb_map, disp_map, acc_map, rgb0, disp0, acc0, z_std, raw = ops.RenderRaysTrainFn.apply(
+            network_fn, network_fine, ray_batch, N_samples, N_importance, lindisp, white_bkgd, t_rand, u,
+            *network_fn.ordered_params(), *network_fine.ordered_params())
+        ret = {'rgb_map': rgb_map, 'disp_map': disp_map, 'acc_map': acc_map}
+        if retraw:
+            ret['raw'] = raw
+        ret.update(rgb0=rgb0, disp0=disp0, acc0=acc0, z_std=z_std)
+        return ret
     z_vals = ops.coarse_z(ray_batch, N_samples, lindisp, t_rand)
 
     query_rays = network_query_fn.from_rays if isinstance(network_query_fn, NetworkQuery) else None

@@ -549,3 +549,39 @@ def test_barrier_timeout_is_reported_on_the_product_paths(cuda, monkeypatch):
     with torch.no_grad():
         again = nb.render(H, W, K, chunk=1024, c2w=c2w, near=2., far=6., **kw)[0]
     assert torch.equal(ok, again)
+
+
+def test_render_rays_training_single_call_equals_op_sequence(cuda, monkeypatch):
+    """nfb_render_rays_train_fwd / nfb_render_rays_bwd (render_rays under autograd as two C calls) against the per-op autograd
+    path they replace (NERFAIL_B200_RENDER_RAYS=ops): the same kernels in the same order, so the eight outputs are
+    bit-identical and the parameter gradients agree up to the order of the L2 float reductions — deterministic and
+    stratified sampling (same torch generator draws), with gradients arriving on rgb only and on all six images."""
+    import nerfail_b200 as nb
+    monkeypatch.setenv("NERFAIL_B200_TRAIN", "bf16")
+    K, _ = synth.intrinsics(30, 30)
+    rays = no.camera_rays(30, 30, K, torch.tensor(synth.pose_spherical(40.0, -30.0, 4.0)[:3, :4]), 2.0, 6.0).to(cuda)
+    g = torch.Generator().manual_seed(3)
+    cots = [torch.randn(s, generator=g).to(cuda) for s in ((700, 3), (700,), (700,), (700, 3), (700,), (700,))]
+    for perturb, n, all_six in ((0., 700, False), (1., 333, True)):
+        runs = []
+        for mode in ("fused", "ops"):
+            monkeypatch.setenv("NERFAIL_B200_RENDER_RAYS", mode)
+            kw_train, _, _, _, _ = nb.create_nerf(Args(), device=cuda)
+            kw_train["network_fn"].load_state_dict(synth.make_non_degenerate(synth.random_state_dict(0), 0))
+            kw_train["network_fine"].load_state_dict(synth.make_non_degenerate(synth.random_state_dict(1), 1))
+            base = {k: v for k, v in kw_train.items() if k not in ("use_viewdirs", "ndc", "perturb")}
+            torch.manual_seed(11)
+            ret = nb.render_rays(rays[:n], retraw=True, perturb=perturb, **base)
+            keys = ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0")
+            loss = sum((ret[k] * c[:n]).sum() for k, c in zip(keys, cots) if all_six or k in ("rgb_map", "rgb0"))
+            loss.backward()
+            for net in (kw_train["network_fn"], kw_train["network_fine"]):
+                net.fused().status()
+            grads = [p.grad.clone() for net in (kw_train["network_fn"], kw_train["network_fine"]) for p in net.ordered_params()]
+            runs.append(({k: ret[k].detach().clone() for k in list(keys) + ["z_std", "raw"]}, grads))
+        (oa, ga), (ob, gb) = runs
+        for k in oa:
+            assert torch.equal(oa[k], ob[k]), (k, perturb)
+        assert len(ga) == len(gb) == 48
+        for a, b in zip(ga, gb):
+            assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-9
