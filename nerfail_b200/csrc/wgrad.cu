@@ -163,6 +163,10 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a0, float a1, float a2, float a3) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(addr), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
@@ -432,6 +436,12 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
       mbar_wait(DONE_B, seg & 1, flag);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int N = 64 * jb.nx, mhalves = jb.ndy / 2;
+      // Flush.  A lane holds 32 consecutive columns of ONE output row (TMEM lane = row): where the destination rows are
+      // 16-byte aligned (ld, col0, cols_valid multiples of 4: the seven 256 x 256 products and feature_linear) they go out
+      // as eight 128-bit L2 reductions per lane, straight from the registers; the odd-pitch products (63-, 319- and
+      // 283-column weights) keep the shared-memory transpose + scalar reductions.  The flush is a fixed cost per (CTA,
+      // product) that the pipeline cannot hide (the accumulators fill TMEM), which is what a small batch pays for.
+      const bool vec = ((jb.ld | jb.col0 | jb.cols_valid) & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.out_w) & 15) == 0;
       for (int mh = 0; mh < mhalves; ++mh) {
         const int row0 = mh * 128 + q * 32;                      // this warp's 32 output rows (TMEM lanes q*32 ..)
         if (row0 >= jb.row_end || row0 + 32 <= jb.row_begin) continue;
@@ -439,6 +449,17 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_kernel(const __grid_constant
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q << 5) << 16) + mh * 256 + c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (vec) {
+            const int row = row0 + lane;
+            if (row >= jb.row_begin && row < jb.row_end) {
+              float* dst = jb.out_w + (int64_t)(row - jb.row_begin) * jb.ld + jb.col0 + c0;
+#pragma unroll
+              for (int t = 0; t < 32; t += 4)
+                if (c0 + t < jb.cols_valid)
+                  red_add_v4_f32(dst + t, __uint_as_float(v[t]), __uint_as_float(v[t + 1]), __uint_as_float(v[t + 2]), __uint_as_float(v[t + 3]));
+            }
+            continue;
+          }
 #pragma unroll
           for (int t = 0; t < 32; ++t) scr[lane * 33 + t] = __uint_as_float(v[t]);
           __syncwarp();
