@@ -67,8 +67,9 @@ NFB_API int nfb_rays_from_batch(const float* rays_o, const float* rays_d, int64_
 
 /* The training loss with its gradient in one pass.
  * replaces: img2mse(rgb, target) + img2mse(rgb0, target) (run_nerf.py:781-789, run_nerf_helpers.py:9) and their autograd.
- * rgb, rgb0 (or NULL), target: n floats; out3 = (loss, mse(rgb), mse(rgb0)); g_rgb / g_rgb0 = 2 (x - target) / n.  */
-NFB_API int nfb_mse_loss2(const float* rgb, const float* rgb0, const float* target, int64_t n, float* out3, float* g_rgb,
+ * rgb, rgb0 (or NULL), target: n floats; out5 = (loss, mse(rgb), mse(rgb0), psnr(rgb), psnr(rgb0)) with psnr = -10 log10(mse)
+ * (mse2psnr, run_nerf_helpers.py:10); g_rgb / g_rgb0 = 2 (x - target) / n.                                              */
+NFB_API int nfb_mse_loss2(const float* rgb, const float* rgb0, const float* target, int64_t n, float* out5, float* g_rgb,
                           float* g_rgb0, void* stream);
 
 /* Coarse depths. replaces: run_nerf.py:357-379 (linspace / lindisp / stratified jitter)

@@ -150,7 +150,7 @@ attack_exchange_kernel(PeerPtrs p, const float4* __restrict__ init, int64_t T, f
 // run_nerf.py:791-800 across G GPUs: flat parameter index space [0, n), this rank owns [i0, i1): mean gradient over ranks,
 // Adam (torch.optim.Adam, no amsgrad / weight decay: the arithmetic of optim.cu's adam_kernel), new parameters to every rank.
 // scalars[0] = lr / (1 - beta1^step), scalars[1] = 1 / sqrt(1 - beta2^step) (device memory: graph replays see the current step).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 adam_exchange_kernel(PeerPtrs p, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t n,
                      const float* __restrict__ scalars, float one_minus_beta1, float beta2, float one_minus_beta2, float eps,
                      float grad_scale,
@@ -317,7 +317,7 @@ int nfb_adam_exchange_step(nfb_peer_t* h, float* exp_avg, float* exp_avg_sq, int
   int rc = nfb_peer_status(h);
   if (rc != NFB_OK) return rc;
   const int64_t per = ((n + 3) / 4 + h->ptrs.G - 1) / h->ptrs.G;
-  nfb::adam_exchange_kernel<<<exchange_grid(per), 256, 0, (cudaStream_t)stream>>>(
+  nfb::adam_exchange_kernel<<<exchange_grid(per, 3), 256, 0, (cudaStream_t)stream>>>(      // 3 CTAs per SM are resident: one wave
       h->ptrs, exp_avg, exp_avg_sq, n, step_scalars, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
       (float)grad_scale,
       h->epoch_ctr, h->cta_counter, h->status_dev);

@@ -85,7 +85,7 @@ __global__ void rays_from_batch_kernel(const float* __restrict__ o, const float*
 }
 
 // loss = img2mse(rgb, target) + img2mse(rgb0, target) (run_nerf.py:781-789, run_nerf_helpers.py:9) with its gradient in the
-// same pass: out[0] = loss, out[1] = mse(rgb), out[2] = mse(rgb0); g = 2 (rgb - target) / n, g0 likewise.  One CTA, fixed
+// same pass: out[0] = loss, out[1] = mse(rgb), out[2] = mse(rgb0), out[3] / out[4] = their PSNR; g = 2 (rgb - target) / n, g0 likewise.  One CTA, fixed
 // reduction order (deterministic); n = 3 R is a few thousand to a few hundred thousand elements.
 __global__ void __launch_bounds__(1024)
 mse_loss2_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0, const float* __restrict__ target, int64_t n,
@@ -114,6 +114,8 @@ mse_loss2_kernel(const float* __restrict__ rgb, const float* __restrict__ rgb0, 
     if (threadIdx.x == 0) {
       const float m = a / (float)n, m0 = b / (float)n;
       out[0] = m + m0; out[1] = m; out[2] = m0;
+      out[3] = -10.f * log10f(m);                       // mse2psnr (run_nerf_helpers.py:10), the two statistics of :783 / :788
+      out[4] = rgb0 ? -10.f * log10f(m0) : 0.f;
     }
   }
 }
@@ -536,10 +538,10 @@ int nfb_rays_from_batch(const float* rays_o, const float* rays_d, int64_t N, flo
   return nfb::check_launch("rays_from_batch");
 }
 
-int nfb_mse_loss2(const float* rgb, const float* rgb0, const float* target, int64_t n, float* out3, float* g_rgb, float* g_rgb0,
+int nfb_mse_loss2(const float* rgb, const float* rgb0, const float* target, int64_t n, float* out5, float* g_rgb, float* g_rgb0,
                   void* stream) {
-  NFB_REQUIRE(rgb && target && out3 && g_rgb && n > 0 && (!rgb0 || g_rgb0), "mse_loss2: bad argument");
-  nfb::mse_loss2_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rgb, rgb0, target, n, out3, g_rgb, g_rgb0);
+  NFB_REQUIRE(rgb && target && out5 && g_rgb && n > 0 && (!rgb0 || g_rgb0), "mse_loss2: bad argument");
+  nfb::mse_loss2_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rgb, rgb0, target, n, out5, g_rgb, g_rgb0);
   return nfb::check_launch("mse_loss2");
 }
 

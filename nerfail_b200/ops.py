@@ -61,13 +61,14 @@ def rays_from_batch(rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far
 
 class MseLoss2Fn(torch.autograd.Function):
     """loss = img2mse(rgb, target) + img2mse(rgb0, target) (run_nerf.py:781-789) with the gradient produced in the forward
-    pass: one kernel instead of ~12 element-wise / reduction launches forward and ~8 backward.  Returns (loss, mse [2])."""
+    pass: one kernel instead of ~12 element-wise / reduction launches forward and ~8 backward.
+    Returns (loss, mse [2], psnr [2]); mse and psnr (mse2psnr, run_nerf_helpers.py:10) are statistics, not differentiable."""
 
     @staticmethod
     def forward(ctx, rgb, rgb0, target):
         rgb, target = _f32(rgb), _f32(target)
         rgb0 = _f32(rgb0) if rgb0 is not None else None
-        out = torch.empty(3, dtype=torch.float32, device=rgb.device)
+        out = torch.empty(5, dtype=torch.float32, device=rgb.device)
         g = torch.empty_like(rgb)
         g0 = torch.empty_like(rgb0) if rgb0 is not None else None
         with torch.cuda.device(rgb.device):
@@ -75,12 +76,12 @@ class MseLoss2Fn(torch.autograd.Function):
                   "nfb_mse_loss2")
         ctx.save_for_backward(g, g0 if g0 is not None else torch.empty(0, device=rgb.device))
         ctx.has0 = g0 is not None
-        mse = out[1:3]
-        ctx.mark_non_differentiable(mse)
-        return out[0], mse
+        mse, psnr = out[1:3], out[3:5]
+        ctx.mark_non_differentiable(mse, psnr)
+        return out[0], mse, psnr
 
     @staticmethod
-    def backward(ctx, g_loss, _g_mse):
+    def backward(ctx, g_loss, _g_mse, _g_psnr):
         g, g0 = ctx.saved_tensors
         return g_loss * g, (g_loss * g0 if ctx.has0 else None), None
 

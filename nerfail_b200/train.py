@@ -13,7 +13,6 @@ identical fused Adam step.
 """
 from __future__ import annotations
 
-import math
 import os
 from typing import Optional, Sequence, Tuple
 
@@ -69,12 +68,6 @@ def sample_ray_batch(images, poses, i_train: Sequence[int], H: int, W: int, K, N
     return torch.stack([rays_o, rays_d], 0), target_s, img_i, torch.stack([rows, cols], -1)
 
 
-def _psnr(mse):
-    """mse2psnr (run_nerf_helpers.py:10) without its host-side torch.Tensor([10.]) (a pageable host-to-device copy cannot
-    be captured in a CUDA graph)."""
-    return torch.log(mse) * (-10.0 / math.log(10.0))
-
-
 def _poll_networks(kw: dict) -> None:
     """Raises if a fused kernel of either network reported a pipeline-barrier time-out so far (no synchronisation: one
     read of pinned host memory per network).  A step whose kernels are still in flight is covered by the next call."""
@@ -99,8 +92,7 @@ def train_step(batch_rays, target_s, H: int, W: int, K, chunk: int, render_kwarg
         rgb, disp, acc, extras = render(H, W, K, chunk=chunk, rays=batch_rays, retraw=True, **kw)
         optimizer.zero_grad()
         # img2mse(fine) + img2mse(coarse) and their gradients in one kernel (run_nerf.py:781-789)
-        loss, mse = ops.MseLoss2Fn.apply(rgb, extras.get("rgb0"), target_s[..., :3])
-        psnr = _psnr(mse)
+        loss, _mse, psnr = ops.MseLoss2Fn.apply(rgb, extras.get("rgb0"), target_s[..., :3])
         out = {"psnr": psnr[0]}
         if "rgb0" in extras:
             out["psnr0"] = psnr[1]

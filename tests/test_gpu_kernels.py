@@ -443,14 +443,15 @@ def test_rays_from_batch_and_fused_mse_loss(cuda):
         ref = torch.mean((a - tgt) ** 2) + torch.mean((a0 - tgt) ** 2)
         ref.backward()
         b, b0 = rgb.to(cuda).requires_grad_(True), rgb0.to(cuda).requires_grad_(True)
-        loss, mse = ops.MseLoss2Fn.apply(b, b0, tgt.to(cuda))
+        loss, mse, psnr = ops.MseLoss2Fn.apply(b, b0, tgt.to(cuda))
+        assert abs(float(psnr[0]) + 10 * np.log10(float(mse[0]))) < 1e-4 and abs(float(psnr[1]) + 10 * np.log10(float(mse[1]))) < 1e-4
         (loss * 1.0).backward()
         assert abs(float(loss) - float(ref)) <= 2e-6 * float(ref) + 1e-9
         assert abs(float(mse[0]) - float(torch.mean((rgb - tgt) ** 2))) <= 2e-6 and abs(float(mse[1]) - float(torch.mean((rgb0 - tgt) ** 2))) <= 2e-6
         assert float((b.grad.cpu() - a.grad).abs().max()) <= 1e-6 * float(a.grad.abs().max()) + 1e-12
         assert float((b0.grad.cpu() - a0.grad).abs().max()) <= 1e-6 * float(a0.grad.abs().max()) + 1e-12
         c = rgb.to(cuda).requires_grad_(True)                                    # no coarse image (N_importance = 0)
-        l1, m1 = ops.MseLoss2Fn.apply(c, None, tgt.to(cuda))
+        l1, m1, _ = ops.MseLoss2Fn.apply(c, None, tgt.to(cuda))
         l1.backward()
         assert abs(float(l1) - float(torch.mean((rgb - tgt) ** 2))) <= 2e-6 and float(m1[1]) == 0.0
 
