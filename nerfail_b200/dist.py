@@ -346,6 +346,9 @@ class PeerAdam:
                     off += k
                 net._grad_sink = self.ex.grad[begin:off]
                 net.invalidate_fused()
+            root = self.ex.grad[:off]                       # the sinks of all networks, contiguous: zeroed with one fill
+            for net in self.nets:
+                net._grad_sink_root = root
         self.params = params
         optimizer.enable_graph_mode(self.device)
 
@@ -386,5 +389,6 @@ class PeerAdam:
                 p.data = p.data.clone()
         for n in self.nets:
             n._grad_sink = None
+            n._grad_sink_root = None
             n.invalidate_fused()
         self.ex.close()

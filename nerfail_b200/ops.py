@@ -69,21 +69,24 @@ class MseLoss2Fn(torch.autograd.Function):
         rgb, target = _f32(rgb), _f32(target)
         rgb0 = _f32(rgb0) if rgb0 is not None else None
         out = torch.empty(5, dtype=torch.float32, device=rgb.device)
-        g = torch.empty_like(rgb)
-        g0 = torch.empty_like(rgb0) if rgb0 is not None else None
+        has0 = rgb0 is not None
+        both = torch.empty((2 if has0 else 1,) + tuple(rgb.shape), dtype=torch.float32, device=rgb.device)   # g | g0: one buffer
         with torch.cuda.device(rgb.device):
-            check(_lib.load().nfb_mse_loss2(ptr(rgb), ptr(rgb0), ptr(target), rgb.numel(), ptr(out), ptr(g), ptr(g0), stream()),
-                  "nfb_mse_loss2")
-        ctx.save_for_backward(g, g0 if g0 is not None else torch.empty(0, device=rgb.device))
-        ctx.has0 = g0 is not None
+            check(_lib.load().nfb_mse_loss2(ptr(rgb), ptr(rgb0), ptr(target), rgb.numel(), ptr(out), ptr(both[0]),
+                                            ptr(both[1]) if has0 else None, stream()), "nfb_mse_loss2")
+        ctx.save_for_backward(both)
+        ctx.has0 = has0
+        ctx.set_materialize_grads(False)           # no zero-filled gradients for the two statistics
         mse, psnr = out[1:3], out[3:5]
         ctx.mark_non_differentiable(mse, psnr)
         return out[0], mse, psnr
 
     @staticmethod
     def backward(ctx, g_loss, _g_mse, _g_psnr):
-        g, g0 = ctx.saved_tensors
-        return g_loss * g, (g_loss * g0 if ctx.has0 else None), None
+        if g_loss is None:
+            return None, None, None
+        scaled = ctx.saved_tensors[0] * g_loss     # both gradients in one launch
+        return scaled[0], (scaled[1] if ctx.has0 else None), None
 
 
 def coarse_z(rays: torch.Tensor, n_samples: int, lindisp: bool = False, t_rand: Optional[torch.Tensor] = None,
@@ -703,10 +706,15 @@ class RenderRaysTrainFn(torch.autograd.Function):
         R, n_samples, n_importance, white, nbytes = ctx.cfg
         dev = rays.device
         flats = []
+        roots = [getattr(net, "_grad_sink_root", None) for net in ctx.nets]
+        shared_root = roots[0] is not None and roots[0] is roots[1]
+        if shared_root:                 # both networks' sinks are slices of one buffer (dist.PeerAdam): one fill
+            roots[0].zero_()
         for net, fused in zip(ctx.nets, ctx.fused):
             sink = getattr(net, "_grad_sink", None)
             if sink is not None:        # data-parallel: the flat gradient lives in NVLink peer memory (dist.PeerAdam)
-                sink.zero_()
+                if not shared_root:
+                    sink.zero_()
                 flats.append(sink)
             else:
                 flats.append(torch.zeros(fused.n_params, dtype=torch.float32, device=dev))
