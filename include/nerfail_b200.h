@@ -41,11 +41,12 @@ extern "C" {
 #define NFB_API
 #endif
 
+/* Library plumbing, no reference counterpart (the reference is eager PyTorch: errors are Python exceptions). */
 NFB_API int         nfb_abi_version(void);
 NFB_API const char* nfb_last_error(void);
-/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+/* number of kernels launched by this library in this process (bench.py's gpu_launches); no reference counterpart */
 NFB_API uint64_t    nfb_launch_count(void);
-/* compute capability of the current device as major*10+minor, or NFB_E_CUDA */
+/* compute capability of the current device as major*10+minor, or NFB_E_CUDA; no reference counterpart */
 NFB_API int         nfb_device_cc(void);
 
 /* ------------------------------------------------------------------------- */
@@ -80,7 +81,8 @@ NFB_API int nfb_coarse_z(const float* rays, int R, int S, int lindisp, const flo
  * tensor): element p = r*S + i is word p & 3 of Philox4x32-10 at counter (p >> 2, stream 0, offset) under key `seed`,
  * mapped to [0,1) with 24 bits like torch.rand.  Same seed + offset -> same depths; advance offset per call.          */
 /* The generator by itself: out[p] for p < n of stream `stream_id` (0 = coarse jitter, 1 = inverse-CDF u); lets a caller or a
- * test reproduce exactly the numbers nfb_coarse_z_rng / nfb_hierarchical_rng consume.                                 */
+ * test reproduce exactly the numbers nfb_coarse_z_rng / nfb_hierarchical_rng consume in place of the torch.rand calls of
+ * run_nerf.py:371 and run_nerf_helpers.py:213.                                                                          */
 NFB_API int nfb_philox_uniform(uint64_t seed, uint64_t offset, uint32_t stream_id, int64_t n, float* out, void* stream);
 NFB_API int nfb_coarse_z_rng(const float* rays, int R, int S, int lindisp, uint64_t seed, uint64_t offset,
                              float* z_vals, void* stream);
@@ -115,12 +117,14 @@ NFB_API int nfb_mlp_fwd(const nfb_mlp_t* h, int mode, const float* pts, const fl
  *   - every launch entry point of the network (nfb_mlp_fwd, nfb_mlp_fwd_train, nfb_mlp_bwd_*, nfb_render_rays_fwd) polls it
  *     first and refuses to run (NFB_E_CUDA) while it is raised, so one time-out cannot silently poison later results.
  * Any number of networks may be alive per device; the 4 constant-memory entries that hold their head weights are shared
- * LRU (a network that lost its entry re-acquires one at its next launch; that costs one host-side wait). */
+ * LRU (a network that lost its entry re-acquires one at its next launch; that costs one host-side wait).
+ * Health / validation / profiling entries: no reference counterpart. */
 NFB_API int nfb_mlp_status(nfb_mlp_t* h);
 NFB_API int nfb_mlp_poll(const nfb_mlp_t* h);
-/* Test hook: raises the flag from the host exactly as a timed-out barrier wait does (no kernel involved). */
+/* Test hook (no reference counterpart): raises the flag from the host exactly as a timed-out barrier wait does. */
 NFB_API int nfb_mlp_debug_raise_abort(nfb_mlp_t* h);
-/* Validation entry: run only the first nsteps (1..10) MMA steps of the fused kernel and dump the fp32
+/* Validation entry (no reference counterpart; the values are NeRF.forward's hidden activations, run_nerf_helpers.py:108-117):
+ * run only the first nsteps (1..10) MMA steps of the fused kernel and dump the fp32
  * post-activation values of the last executed step to dbg [R*S,256] (128 columns for the view layer).     */
 NFB_API int nfb_mlp_fwd_debug(const nfb_mlp_t* h, int mode, const float* pts, const float* dirs,
                       const float* rays, const float* z_vals, int R, int S, float* raw, int nsteps, float* dbg,
@@ -150,7 +154,7 @@ NFB_API int nfb_mlp_bwd_weights(const nfb_mlp_t* h, const void* act_img, const v
 NFB_API int nfb_mlp_bwd(const nfb_mlp_t* h, const float* g_raw, int64_t M, const uint32_t* mask, const void* act_img,
                         void* dy_img, float* grad, int* ready, void* stream);
 
-/* Profiling aid: the full forward (mode 1) while CTA 0 records a timeline of its barrier waits into
+/* Profiling aid (no reference counterpart): the full forward (mode 1) while CTA 0 records a timeline of its barrier waits into
  * trace [3 roles][2048 events][4] uint64 = (tag, clock begin, clock end, aux); roles: 0 weight producer, 1 MMA warp,
  * 2 epilogue warps.  scripts/trace_mlp.py decodes it.                                                     */
 NFB_API int nfb_mlp_fwd_trace(const nfb_mlp_t* h, const float* rays, const float* z_vals, int R, int S, float* raw,
@@ -199,7 +203,7 @@ typedef struct nfb_adam_tensor {
 } nfb_adam_tensor;
 NFB_API int nfb_adam_step(const nfb_adam_tensor* tensors, int count, int64_t step, double lr, double beta1, double beta2,
                           double eps, double grad_scale, void* stream);
-/* CUDA-graph form of the same update: the two step-dependent constants (lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step);
+/* CUDA-graph form of the same update (optimizer.step() of run_nerf.py:792): the two step-dependent constants (lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step);
  * nfb_adam_step_scalars computes them on the host exactly as nfb_adam_step does) are read from step_scalars [2] in device
  * memory when the kernel RUNS, so a captured training step is replayed with the current step and learning rate. */
 NFB_API int nfb_adam_step_scalars(int64_t step, double lr, double beta1, double beta2, float* out2);
@@ -215,7 +219,8 @@ NFB_API int nfb_composite_fwd(const float* raw, const float* z_vals, const float
                       const float* noise, int R, int S, int white_bkgd,
                       float* rgb_map, float* disp, float* acc, float* weights, float* depth,
                       float* pts_max, void* stream);
-/* Analytic backward of the above (suffix-sum form). Any g_* may be NULL (= zero). g_raw out [R,S,4]. */
+/* Analytic backward of the above (suffix-sum form): what autograd derives for run_nerf.py:262-305 when loss.backward()
+ * (run_nerf.py:790) runs.  Any g_* may be NULL (= zero). g_raw out [R,S,4]. */
 NFB_API int nfb_composite_bwd(const float* raw, const float* z_vals, const float* rays_d, int ray_pitch,
                       const float* noise, int R, int S, int white_bkgd,
                       const float* g_rgb, const float* g_disp, const float* g_acc,
@@ -311,8 +316,8 @@ NFB_API int nfb_gauss_weights(const float* dist_idx, int64_t B, int64_t HW, floa
 NFB_API int nfb_gauss_gather_fwd(const float* table, int64_t T, const float* w_idx, const uint8_t* ori,
                          int64_t B, int64_t HW, float eps, float* x, float* x_rgba, float* minmax,
                          void* stream);
-/* Backward of the above w.r.t. table: one red.global.add.v4.f32 per (pixel, neighbour) straight into the L2-resident
- * table.  (north_star asks for warp-aggregated atomics; the match.any merge of equal rows was built and measured SLOWER
+/* Backward of the above w.r.t. table (autograd of model/GaussNet.py:53-119 under total_loss.backward(),
+ * attack_NeRFail_S.py:346): one red.global.add.v4.f32 per (pixel, neighbour) straight into the L2-resident table.  (north_star asks for warp-aggregated atomics; the match.any merge of equal rows was built and measured SLOWER
  * on B200 — 64-73 us against 42-47 us per 800x800 view, the L2 atomic units absorb duplicates faster than eight
  * match.any rounds per pixel remove them — so it is opt-in, NERFAIL_B200_SCATTER_AGG=1; csrc/gauss.cu.)
  * g_x, g_xrgba [B,HW,4] (either may be NULL); x is the saved forward output; g_table [T,4] is
@@ -375,7 +380,9 @@ NFB_API int nfb_attack_sign_step(float* table, const float* init, const int64_t*
 /* C. Multi-GPU exchange steps over NVLink peer memory (one process per GPU)   */
 /* ------------------------------------------------------------------------- */
 
-/* Peer memory: a cudaMalloc allocation (zero-filled) that the other ranks of the node open through a 64-byte CUDA IPC handle
+/* Peer memory (no reference counterpart: the reference is single-process; the steps built on it replace
+ * attack_NeRFail_S.py:348-392 and run_nerf.py:791-792 of a data-parallel run): a cudaMalloc allocation (zero-filled) that
+ * the other ranks of the node open through a 64-byte CUDA IPC handle
  * (exchanged by the host side, e.g. torch.distributed.all_gather_object); peer access is enabled on first open.
  * nfb_peer_create binds, for a group of G <= 8 ranks, every rank's gradient buffer, every rank's copy of the quantity
  * being updated and every rank's flag words (nfb_peer_flag_bytes() bytes, zero-filled) — arrays of G pointers indexed by

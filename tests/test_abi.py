@@ -28,6 +28,22 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert _lib.load().nfb_abi_version() == 2
 
 
+def test_every_declared_symbol_cites_the_reference_interface_it_replaces():
+    """include/nerfail_b200.h: the comment that governs each NFB_API declaration names the reference file:line the entry
+    point replaces, or says that it has no reference counterpart (plumbing, validation and profiling entries)."""
+    text = re.sub(r"(?m)^#.*$", "", open(os.path.join(REPO, "include", "nerfail_b200.h")).read())   # drop #define NFB_API ...
+    last, bad, n = "", [], 0
+    for m in re.finditer(r"/\*(.*?)\*/|(NFB_API[^;]*;)", text, re.S):
+        if m.group(1) is not None:
+            last = m.group(1)
+            continue
+        n += 1
+        name = re.search(r"\b(nfb_\w+)\s*\(", m.group(2)).group(1)
+        if not (re.search(r"\w+\.py:\d+", last) or "no reference counterpart" in last):
+            bad.append(name)
+    assert n == len(header_symbols()) and not bad, bad
+
+
 def test_error_reporting_without_compute():
     from nerfail_b200 import _lib
     lib = _lib.load()
